@@ -1,0 +1,187 @@
+// .basis container layer of the C ABI: header / slice-descriptor parsing, CRC-16 checks and the
+// per-format slice loops of the reference's file-level API (src/basis.rs:8-372, :419-572),
+// re-designed around the device: every slice of a file is uploaded once into 256-byte aligned
+// device regions, all slice kernels are enqueued back to back on one stream, and the results
+// come back with one copy per image.  Parsing and CRC stay on the host, as in the reference.
+#include <cstring>
+#include <vector>
+
+#include "../../include/b2bu.h"
+#include "host_internal.h"
+#include "kernels.h"
+#include "etc1s_host.h"
+
+namespace b2bu {
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+static uint32_t rd_le(const uint8_t* p, int n)
+{
+    uint32_t v = 0;
+    for (int i = 0; i < n; i++) v |= (uint32_t)p[i] << (8 * i);
+    return v;
+}
+
+// basis.rs:364-372 crc16 -- table-driven form of the same polynomial step (one lookup per byte):
+// the reference's q/k update is exactly crc = (crc << 8) ^ T[(crc >> 8) ^ b] with T[q] = k ^ k<<5 ^ k<<12.
+static uint16_t g_crc_table[256];
+static std::once_flag g_crc_once;
+static void crc_init()
+{
+    for (unsigned q = 0; q < 256; q++) {
+        const uint16_t k = (uint16_t)((q >> 4) ^ q);
+        g_crc_table[q] = (uint16_t)(k ^ (k << 5) ^ (k << 12));
+    }
+}
+uint16_t crc16_host(const uint8_t* r, size_t n, uint16_t crc)
+{
+    std::call_once(g_crc_once, crc_init);
+    crc = (uint16_t)~crc;
+    for (size_t i = 0; i < n; i++) crc = (uint16_t)((crc << 8) ^ g_crc_table[(uint8_t)(r[i] ^ (crc >> 8))]);
+    return (uint16_t)~crc;
+}
+
+// basis.rs:554-571 SliceDesc::from_file_bytes
+static SliceDesc parse_slice_desc(const uint8_t* p)
+{
+    SliceDesc s;
+    s.image_index = rd_le(p, 3); s.level_index = p[3]; s.flags = p[4];
+    s.orig_width = rd_le(p + 5, 2); s.orig_height = rd_le(p + 7, 2);
+    s.num_blocks_x = rd_le(p + 9, 2); s.num_blocks_y = rd_le(p + 11, 2);
+    s.file_ofs = rd_le(p + 13, 4); s.file_size = rd_le(p + 17, 4); s.crc = rd_le(p + 21, 2);
+    return s;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace b2bu
+
+using namespace b2bu;
+
+extern "C" {
+
+uint16_t b2bu_crc16(const uint8_t* data, size_t len, uint16_t crc) { return crc16_host(data, len, crc); }
+
+int b2bu_read_header(const uint8_t* buf, size_t len, b2bu_header* h)
+{
+    if (!buf || !h) return B2BU_ERR_ARGUMENT;
+    if (len < 2 || rd_le(buf, 2) != 0x4273) return B2BU_ERR_SIG;                    // basis.rs:308-310
+    if (len < 77) return B2BU_ERR_HEADER_SIZE;                                      // basis.rs:312-318
+    static const uint8_t widths[26] = {2, 2, 2, 2, 4, 2, 3, 3, 1, 2, 1, 3, 4, 4, 4, 2, 4, 3, 2, 4, 3, 4, 4, 4, 4, 4};
+    uint32_t* f = reinterpret_cast<uint32_t*>(h);                                   // basis.rs:475-516
+    size_t pos = 0;
+    for (int i = 0; i < 26; i++) { f[i] = rd_le(buf + pos, widths[i]); pos += widths[i]; }
+    if (h->header_size != 77) return B2BU_ERR_HEADER_SIZE;                          // basis.rs:322-328
+    if (crc16_host(buf + 8, 77 - 8, 0) != h->header_crc16) return B2BU_ERR_HEADER_CRC;   // basis.rs:330-333
+    return B2BU_OK;
+}
+
+int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header, b2bu_image* images, uint32_t max_images,
+                 uint32_t* num_images, uint8_t* out, uint64_t out_cap, uint64_t* out_needed)
+{
+    if (num_images) *num_images = 0;
+    if (out_needed) *out_needed = 0;
+    if (target < B2BU_RGBA || target > B2BU_UASTC) return B2BU_ERR_ARGUMENT;
+    b2bu_header h;
+    int st = b2bu_read_header(buf, len, &h);
+    if (st) return st;
+    if (header) *header = h;
+    if (crc16_host(buf + 77, len - 77, 0) != h.data_crc16) return B2BU_ERR_DATA_CRC;   // basis.rs:338-341
+    // basis.rs:343-362 read_slice_descs
+    std::vector<SliceDesc> descs(h.total_slices);
+    for (uint32_t i = 0; i < h.total_slices; i++) {
+        const size_t start = (size_t)h.slice_desc_file_ofs + (size_t)i * 23;
+        if (start > len) return B2BU_ERR_RANGE;                                     // reference: slice index panic
+        if (len - start < 23) return B2BU_ERR_SLICE_DESC;
+        descs[i] = parse_slice_desc(buf + start);
+        if ((uint64_t)descs[i].file_ofs + descs[i].file_size > len) return B2BU_ERR_RANGE;   // basis.rs:549-551 panics
+    }
+    if (h.tex_format > 1) return B2BU_ERR_TEX_FORMAT;                               // basis.rs:403-412
+    const bool etc1s = h.tex_format == 0;
+    const bool has_alpha = (h.flags & 4u) != 0;
+    if (etc1s && target != B2BU_RGBA && target != B2BU_ETC1) return B2BU_ERR_UNIMPLEMENTED;   // basis.rs:171,200,229,258
+    if (etc1s && has_alpha && (h.total_slices % 2) != 0) return B2BU_ERR_ALPHA_SLICES;       // basis.rs:18-20
+
+    // ---- plan the images -----------------------------------------------------------------
+    const bool pair = etc1s && has_alpha && target == B2BU_RGBA;    // basis.rs:24-51 pairs rgb+alpha; read_to_etc1 does not
+    const uint32_t nimg = pair ? h.total_slices / 2 : h.total_slices;
+    std::vector<b2bu_image> plan(nimg);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < nimg; i++) {
+        const SliceDesc& s = descs[pair ? 2 * i : i];
+        if (pair) {
+            const SliceDesc& a = descs[2 * i + 1];
+            if (!(a.flags & 1u)) return B2BU_ERR_ALPHA_SLICES;                      // "Expected slice with alpha"
+            if (a.num_blocks_x != s.num_blocks_x || a.num_blocks_y != s.num_blocks_y) return B2BU_ERR_ALPHA_SLICES;
+        }
+        b2bu_image& im = plan[i];
+        im.w = s.orig_width; im.h = s.orig_height; im.reserved = 0; im.offset = total;
+        if (etc1s) {
+            const uint64_t nb = (uint64_t)s.num_blocks_x * s.num_blocks_y;
+            if (target == B2BU_RGBA) { im.nbytes = nb * 64; im.stride = 16u * s.orig_width; }   // basis.rs:43-49 (quirk C-6)
+            else { im.nbytes = nb * 8; im.stride = 8u * s.num_blocks_x; }                        // basis.rs:117-121
+        } else if (target == B2BU_UASTC) {
+            im.nbytes = s.file_size; im.stride = 16u * s.num_blocks_x;                           // basis.rs:189-193
+        } else {
+            if (s.file_size % 16 != 0) return B2BU_ERR_LENGTH;
+            const uint64_t nb = s.file_size / 16;
+            if (target == B2BU_RGBA && (s.num_blocks_x == 0 || nb % s.num_blocks_x != 0)) return B2BU_ERR_RANGE;
+            im.nbytes = nb * b2bu_block_bytes(target);
+            im.stride = (uint32_t)b2bu_block_bytes(target) * s.num_blocks_x;                     // basis.rs:78-84,131-135
+        }
+        total += im.nbytes;
+    }
+    if (num_images) *num_images = nimg;
+    if (out_needed) *out_needed = total;
+    if (images) for (uint32_t i = 0; i < nimg && i < max_images; i++) images[i] = plan[i];
+    if (!out) return B2BU_OK;
+    if (out_cap < total) return B2BU_ERR_ARGUMENT;
+    if (nimg == 0) return B2BU_OK;
+
+    if (!etc1s && target == B2BU_UASTC) {                                           // uastc.rs:85-87: plain copy
+        for (uint32_t i = 0; i < nimg; i++) memcpy(out + plan[i].offset, buf + descs[i].file_ofs, descs[i].file_size);
+        return B2BU_OK;
+    }
+    if (etc1s) return etc1s_read_file(target, buf, len, h, descs.data(), plan.data(), nimg, pair, out);
+
+    // ---- UASTC file: upload every slice once, launch all, copy back -------------------------
+    DeviceCtx* c;
+    if ((st = get_ctx(&c))) return st;
+    std::lock_guard<std::mutex> lk(c->run_mu);
+    size_t in_total = 0;
+    std::vector<size_t> in_ofs(nimg), out_ofs(nimg);
+    size_t out_total = 0;
+    for (uint32_t i = 0; i < nimg; i++) {
+        in_ofs[i] = in_total; in_total += align_up(descs[i].file_size, 256);
+        out_ofs[i] = out_total; out_total += align_up(plan[i].nbytes, 256);
+    }
+    if ((st = ensure(&c->d_in[0], &c->in_cap[0], in_total))) return st;
+    if ((st = ensure(&c->d_out[0], &c->out_cap[0], out_total))) return st;
+    cudaStream_t s0 = c->streams[0], s1 = c->streams[1];
+    uint8_t* d_in = static_cast<uint8_t*>(c->d_in[0]);
+    uint8_t* d_out = static_cast<uint8_t*>(c->d_out[0]);
+    CK(cudaMemsetAsync(c->d_err, 0xFF, sizeof(unsigned long long), s0));
+    // one status word per file would lose which slice failed first in file order, so slices are
+    // given disjoint index ranges: index_base = blocks of all earlier slices
+    uint64_t base = 0;
+    std::vector<cudaEvent_t> done(nimg);
+    for (uint32_t i = 0; i < nimg; i++) {
+        const uint64_t nb = descs[i].file_size / 16;
+        CK(cudaMemcpyAsync(d_in + in_ofs[i], buf + descs[i].file_ofs, descs[i].file_size, cudaMemcpyHostToDevice, s0));
+        CK(launch_uastc_transcode(target, d_in + in_ofs[i], d_out + out_ofs[i], nb, descs[i].num_blocks_x, base, c->d_err, c->sm_count, s0));
+        count_launch(1);
+        base += nb;
+        // copy back on a second stream so that it overlaps the next slice's upload and kernel
+        CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        CK(cudaEventRecord(done[i], s0));
+        CK(cudaStreamWaitEvent(s1, done[i], 0));
+        CK(cudaMemcpyAsync(out + plan[i].offset, d_out + out_ofs[i], plan[i].nbytes, cudaMemcpyDeviceToHost, s1));
+    }
+    CK(cudaStreamSynchronize(s0));
+    CK(cudaStreamSynchronize(s1));
+    for (uint32_t i = 0; i < nimg; i++) cudaEventDestroy(done[i]);
+    CK(cudaMemcpy(c->h_err, c->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return decode_status_word(*c->h_err, nullptr);
+}
+
+}  // extern "C"

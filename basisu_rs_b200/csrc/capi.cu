@@ -1,0 +1,239 @@
+// C ABI (include/b2bu.h) + host runtime: per-device context, scratch buffers, streams, the
+// chunked H2D -> kernel -> D2H pipeline of the host-pointer entry points, error mapping.
+// Host-side counterpart of the reference's crate-private slice API (src/uastc.rs:77-165) and of
+// its single-block API (src/lib.rs:29-53).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b2bu.h"
+#include "host_internal.h"
+#include "kernels.h"
+
+namespace b2bu {
+
+static thread_local int t_device = 0;
+static thread_local char t_cuda_err[256] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static DeviceCtx g_ctx[kMaxDevices];
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    snprintf(t_cuda_err, sizeof t_cuda_err, "%s: %s", what, cudaGetErrorString(e));
+    return B2BU_ERR_CUDA;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int get_ctx(DeviceCtx** out)
+{
+    const int dev = t_device;
+    if (dev < 0 || dev >= kMaxDevices) return B2BU_ERR_ARGUMENT;
+    DeviceCtx& c = g_ctx[dev];
+    std::lock_guard<std::mutex> lk(c.init_mu);
+    CK(cudaSetDevice(dev));
+    if (!c.ready) {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, dev));
+        c.device = dev;
+        c.sm_count = prop.multiProcessorCount;
+        CK(upload_tables());
+        for (int i = 0; i < kStreams; i++) CK(cudaStreamCreateWithFlags(&c.streams[i], cudaStreamNonBlocking));
+        CK(cudaMalloc(&c.d_err, sizeof(unsigned long long)));
+        CK(cudaMallocHost(&c.h_err, sizeof(unsigned long long)));
+        c.ready = true;
+    }
+    *out = &c;
+    return B2BU_OK;
+}
+
+int ensure(void** p, size_t* cap, size_t need)
+{
+    if (*cap >= need) return B2BU_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    size_t want = need + need / 4 + 4096;
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) { want = need; e = cudaMalloc(p, want); }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
+    *cap = want;
+    return B2BU_OK;
+}
+
+int decode_status_word(unsigned long long w, uint64_t* first_bad)
+{
+    if (w == ~0ull) { if (first_bad) *first_bad = ~0ull; return B2BU_OK; }
+    if (first_bad) *first_bad = (uint64_t)(w >> 8);
+    const unsigned code = (unsigned)(w & 0xFF);
+    return code == ERR_MODE_DEV ? B2BU_ERR_MODE : code == ERR_PATTERN_DEV ? B2BU_ERR_PATTERN : B2BU_ERR_CUDA;
+}
+
+// Host-pointer UASTC path: chunks of whole block rows, round-robin over kStreams streams so that
+// the H2D copy of chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap.
+static int uastc_host_run(int target, const uint8_t* blocks, size_t nblocks, size_t bpr, uint8_t* out, uint64_t* first_bad)
+{
+    DeviceCtx* c;
+    int st = get_ctx(&c);
+    if (st) return st;
+    std::lock_guard<std::mutex> lk(c->run_mu);
+    const size_t ob = b2bu_block_bytes(target);
+    size_t chunk = kChunkBlocks;
+    if (target == B2BU_RGBA) {                           // whole block rows keep the output contiguous
+        chunk = (kChunkBlocks / bpr) * bpr;
+        if (chunk == 0) chunk = bpr;
+    }
+    if (chunk > nblocks) chunk = nblocks;
+    for (int s = 0; s < kStreams; s++) {
+        if ((st = ensure(&c->d_in[s], &c->in_cap[s], chunk * 16))) return st;
+        if ((st = ensure(&c->d_out[s], &c->out_cap[s], chunk * ob))) return st;
+    }
+    CK(cudaMemsetAsync(c->d_err, 0xFF, sizeof(unsigned long long), c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[0]));
+    size_t done = 0;
+    int ci = 0;
+    while (done < nblocks) {
+        const size_t n = nblocks - done < chunk ? nblocks - done : chunk;
+        const int s = ci % kStreams;
+        cudaStream_t stream = c->streams[s];
+        CK(cudaMemcpyAsync(c->d_in[s], blocks + done * 16, n * 16, cudaMemcpyHostToDevice, stream));
+        CK(launch_uastc_transcode(target, c->d_in[s], c->d_out[s], n, (uint32_t)bpr, done, c->d_err, c->sm_count, stream));
+        count_launch(1);
+        CK(cudaMemcpyAsync(out + done * ob, c->d_out[s], n * ob, cudaMemcpyDeviceToHost, stream));
+        done += n;
+        ci++;
+    }
+    for (int s = 0; s < kStreams; s++) CK(cudaStreamSynchronize(c->streams[s]));
+    CK(cudaMemcpy(c->h_err, c->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return decode_status_word(*c->h_err, first_bad);
+}
+
+}  // namespace b2bu
+
+using namespace b2bu;
+
+extern "C" {
+
+const char* b2bu_error_string(int status)
+{
+    switch (status) {
+    case B2BU_OK: return "ok";
+    case B2BU_ERR_LENGTH: return "data length is not divisible by UASTC block size (16)";
+    case B2BU_ERR_MODE: return "invalid mode index";
+    case B2BU_ERR_PATTERN: return "block pattern is not valid";
+    case B2BU_ERR_HUFFMAN: return "invalid Huffman table or code (see huffman.rs:85-106,177,193)";
+    case B2BU_ERR_SELECTOR_CB: return "Global/Hybrid selector codebooks are not supported";
+    case B2BU_ERR_PREDICTION: return "malformed ETC1S prediction (reference panics)";
+    case B2BU_ERR_VLC: return "VLC value overflow (reference panics)";
+    case B2BU_ERR_RANGE: return "section, slice or codebook index out of range (reference panics)";
+    case B2BU_ERR_SIG: return "Sig mismatch, not a Basis Universal file";
+    case B2BU_ERR_HEADER_SIZE: return "unexpected header size";
+    case B2BU_ERR_HEADER_CRC: return "Header CRC16 failed";
+    case B2BU_ERR_DATA_CRC: return "Data CRC16 failed";
+    case B2BU_ERR_TEX_FORMAT: return "Unknown texture format";
+    case B2BU_ERR_UNIMPLEMENTED: return "not implemented for this texture format (reference: unimplemented!())";
+    case B2BU_ERR_ALPHA_SLICES: return "alpha slice layout is invalid";
+    case B2BU_ERR_SLICE_DESC: return "slice description array is truncated";
+    case B2BU_ERR_ARGUMENT: return "invalid argument";
+    case B2BU_ERR_CUDA: return "CUDA error";
+    default: return "unknown status";
+    }
+}
+
+const char* b2bu_last_cuda_error(void) { return t_cuda_err; }
+
+int b2bu_device_count(int* count)
+{
+    if (!count) return B2BU_ERR_ARGUMENT;
+    CK(cudaGetDeviceCount(count));
+    return B2BU_OK;
+}
+
+int b2bu_init(int device)
+{
+    if (device < 0 || device >= kMaxDevices) return B2BU_ERR_ARGUMENT;
+    t_device = device;
+    DeviceCtx* c;
+    return get_ctx(&c);
+}
+
+size_t b2bu_block_bytes(int target) { return target == B2BU_RGBA ? 64 : target == B2BU_ETC1 ? 8 : 16; }
+
+void* b2bu_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaSetDevice(t_device) != cudaSuccess) return nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void b2bu_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+uint64_t b2bu_launch_count(void) { return g_launches.load(); }
+
+int b2bu_uastc_transcode(int target, const uint8_t* blocks, size_t nbytes, uint8_t* out, size_t out_bytes, uint64_t* first_bad_block)
+{
+    if (first_bad_block) *first_bad_block = ~0ull;
+    if (target < B2BU_ASTC || target > B2BU_ETC2) return B2BU_ERR_ARGUMENT;
+    if (nbytes % 16 != 0) return B2BU_ERR_LENGTH;                                  // uastc.rs:55-56
+    const size_t n = nbytes / 16;
+    if (n == 0) return B2BU_OK;
+    if (!blocks || !out || out_bytes < n * b2bu_block_bytes(target)) return B2BU_ERR_ARGUMENT;
+    return uastc_host_run(target, blocks, n, 1, out, first_bad_block);
+}
+
+int b2bu_uastc_decode_rgba(const uint8_t* blocks, size_t nbytes, size_t blocks_per_row, uint32_t* out_pixels,
+                           size_t out_pixel_count, uint64_t* first_bad_block)
+{
+    if (first_bad_block) *first_bad_block = ~0ull;
+    if (nbytes % 16 != 0) return B2BU_ERR_LENGTH;
+    const size_t n = nbytes / 16;
+    if (n == 0) return B2BU_OK;
+    if (!blocks || !out_pixels || blocks_per_row == 0 || n % blocks_per_row != 0 || out_pixel_count < n * 16) return B2BU_ERR_ARGUMENT;
+    return uastc_host_run(B2BU_RGBA, blocks, n, blocks_per_row, reinterpret_cast<uint8_t*>(out_pixels), first_bad_block);
+}
+
+int b2bu_unpack_uastc_block_to_rgba(const uint8_t in[16], uint32_t out[16]) { return b2bu_uastc_decode_rgba(in, 16, 1, out, 16, nullptr); }
+int b2bu_transcode_uastc_block_to_astc(const uint8_t in[16], uint8_t out[16]) { return b2bu_uastc_transcode(B2BU_ASTC, in, 16, out, 16, nullptr); }
+int b2bu_transcode_uastc_block_to_bc7(const uint8_t in[16], uint8_t out[16]) { return b2bu_uastc_transcode(B2BU_BC7, in, 16, out, 16, nullptr); }
+int b2bu_transcode_uastc_block_to_etc1(const uint8_t in[16], uint8_t out[8]) { return b2bu_uastc_transcode(B2BU_ETC1, in, 16, out, 8, nullptr); }
+int b2bu_transcode_uastc_block_to_etc2(const uint8_t in[16], uint8_t out[16]) { return b2bu_uastc_transcode(B2BU_ETC2, in, 16, out, 16, nullptr); }
+
+int b2bu_uastc_transcode_dev(int target, const void* d_blocks, size_t nbytes, size_t blocks_per_row, void* d_out,
+                             size_t out_bytes, void* d_status, void* stream)
+{
+    if (target < B2BU_RGBA || target > B2BU_ETC2) return B2BU_ERR_ARGUMENT;
+    if (nbytes % 16 != 0) return B2BU_ERR_LENGTH;
+    const size_t n = nbytes / 16;
+    if (n == 0) return B2BU_OK;
+    if (!d_blocks || !d_out || !d_status || out_bytes < n * b2bu_block_bytes(target)) return B2BU_ERR_ARGUMENT;
+    if (target == B2BU_RGBA && (blocks_per_row == 0 || n % blocks_per_row != 0)) return B2BU_ERR_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(d_blocks) | reinterpret_cast<uintptr_t>(d_out)) & 15) return B2BU_ERR_ARGUMENT;
+    DeviceCtx* c;
+    int st = get_ctx(&c);
+    if (st) return st;
+    CK(launch_uastc_transcode(target, d_blocks, d_out, n, (uint32_t)(blocks_per_row ? blocks_per_row : 1), 0,
+                              reinterpret_cast<unsigned long long*>(d_status), c->sm_count, reinterpret_cast<cudaStream_t>(stream)));
+    count_launch(1);
+    return B2BU_OK;
+}
+
+int b2bu_status_reset_dev(void* d_status, void* stream)
+{
+    if (!d_status) return B2BU_ERR_ARGUMENT;
+    CK(cudaMemsetAsync(d_status, 0xFF, 8, reinterpret_cast<cudaStream_t>(stream)));
+    return B2BU_OK;
+}
+
+int b2bu_status_read_dev(const void* d_status, void* stream, uint64_t* first_bad_block)
+{
+    if (!d_status) return B2BU_ERR_ARGUMENT;
+    unsigned long long w = 0;
+    CK(cudaMemcpyAsync(&w, d_status, 8, cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(stream)));
+    CK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+    return decode_status_word(w, first_bad_block);
+}
+
+}  // extern "C"

@@ -1,0 +1,37 @@
+// Host-runtime internals shared by capi.cu, basis_file.cu and etc1s_host.cu.
+#pragma once
+#include <cstdint>
+#include <mutex>
+#include <cuda_runtime.h>
+
+namespace b2bu {
+
+constexpr int kMaxDevices = 16;
+constexpr int kStreams = 3;                      // H2D / kernel / D2H of consecutive chunks overlap
+constexpr size_t kChunkBlocks = size_t(1) << 19; // 8 MiB of UASTC per pipeline stage
+
+enum { ERR_MODE_DEV = 2, ERR_PATTERN_DEV = 3 };  // == ERR_MODE / ERR_PATTERN in uastc_device.cuh
+
+struct DeviceCtx {
+    std::mutex init_mu, run_mu;
+    bool ready = false;
+    int device = 0, sm_count = 0;
+    cudaStream_t streams[kStreams] = {};
+    void* d_in[kStreams] = {};
+    size_t in_cap[kStreams] = {};
+    void* d_out[kStreams] = {};
+    size_t out_cap[kStreams] = {};
+    unsigned long long* d_err = nullptr;          // one status word, atomicMin'ed by every launch of a call
+    unsigned long long* h_err = nullptr;          // pinned
+};
+
+// basis.rs:520-535
+struct SliceDesc { uint32_t image_index, level_index, flags, orig_width, orig_height, num_blocks_x, num_blocks_y, file_ofs, file_size, crc; };
+
+int get_ctx(DeviceCtx** out);
+int ensure(void** p, size_t* cap, size_t need);
+int cuda_fail(cudaError_t e, const char* what);
+int decode_status_word(unsigned long long w, uint64_t* first_bad);
+void count_launch(uint64_t n);
+
+}  // namespace b2bu

@@ -1,0 +1,1009 @@
+// UASTC 4x4 block front-end + the five target back-ends as mode-specialised device code.
+//
+// Design (B200-first, not a port): the reference walks every block with a bit-at-a-time reader
+// (src/bitreader.rs) and byte-at-a-time writers (src/bitwriter.rs).  Here one thread owns one
+// 16-byte block held in four registers; every UASTC mode is a template instantiation whose field
+// offsets are compile-time constants, so a field read is one funnel shift + mask, the weight
+// stream is handled as a whole 64/96-bit word (SWAR), and the output block is assembled in four
+// registers and stored with one 128-bit store.  Tables that are indexed by per-thread data live
+// in shared memory (DevTables).
+//
+// Reference behaviour being reproduced (paths relative to /root/reference/src):
+//   uastc.rs:237-327 decode_block_to_rgba     target_formats/astc.rs:8-181
+//   target_formats/bc7.rs:9-553               target_formats/etc.rs:11-341
+#pragma once
+#include <cstdint>
+#ifndef B2BU_HOST_EMU   // tests/emu compiles this header for the host with shimmed intrinsics
+#include <cuda_runtime.h>
+#endif
+#include "device_tables.h"
+
+namespace b2bu {
+
+enum { FMT_RGB = 0, FMT_RGBA = 1, FMT_LA = 2 };
+enum { TGT_RGBA = 0, TGT_ASTC = 1, TGT_BC7 = 2, TGT_ETC1 = 3, TGT_ETC2 = 4 };
+enum { ERR_OK = 0, ERR_LEN = 1, ERR_MODE = 2, ERR_PATTERN = 3 };
+
+#define B2BU_DI __device__ __forceinline__
+
+// ------------------------------------------------------------------------------------------
+// Mode descriptors (uastc.rs:528-557) and everything derivable from them at compile time.
+// ------------------------------------------------------------------------------------------
+template <int M> struct MI;
+#define B2BU_MODE(M, CS, R, F, WB, PL, SS, FL)                                                   \
+    template <> struct MI<M> {                                                                   \
+        static constexpr int code_size = CS, range = R, fmt = F, wbits = WB, planes = PL,       \
+                             subsets = SS, flags_bits = FL;                                      \
+    };
+B2BU_MODE(0, 4, 19, FMT_RGB, 4, 1, 1, 15)
+B2BU_MODE(1, 6, 20, FMT_RGB, 2, 1, 1, 15)
+B2BU_MODE(2, 5, 8, FMT_RGB, 3, 1, 2, 15)
+B2BU_MODE(3, 5, 7, FMT_RGB, 2, 1, 3, 15)
+B2BU_MODE(4, 5, 12, FMT_RGB, 2, 1, 2, 15)
+B2BU_MODE(5, 5, 20, FMT_RGB, 3, 1, 1, 15)
+B2BU_MODE(6, 5, 18, FMT_RGB, 2, 2, 1, 15)
+B2BU_MODE(7, 5, 12, FMT_RGB, 2, 1, 2, 15)
+B2BU_MODE(9, 5, 8, FMT_RGBA, 2, 1, 2, 23)
+B2BU_MODE(10, 3, 13, FMT_RGBA, 4, 1, 1, 17)
+B2BU_MODE(11, 2, 13, FMT_RGBA, 2, 2, 1, 17)
+B2BU_MODE(12, 3, 19, FMT_RGBA, 3, 1, 1, 17)
+B2BU_MODE(13, 5, 20, FMT_RGBA, 1, 2, 1, 23)
+B2BU_MODE(14, 5, 20, FMT_RGBA, 2, 1, 1, 23)
+B2BU_MODE(15, 7, 20, FMT_LA, 4, 1, 1, 23)
+B2BU_MODE(16, 6, 20, FMT_LA, 2, 1, 2, 23)
+B2BU_MODE(17, 6, 20, FMT_LA, 2, 2, 1, 23)
+B2BU_MODE(18, 4, 11, FMT_RGB, 5, 1, 1, 15)
+#undef B2BU_MODE
+
+__host__ __device__ constexpr int range_bits(int r) { return r == 7 ? 2 : r == 8 ? 4 : r == 11 ? 5 : r == 12 ? 3 : r == 13 ? 4 : r == 18 ? 5 : r == 19 ? 6 : 8; }
+__host__ __device__ constexpr int range_tq(int r) { return (r == 7 || r == 13 || r == 19) ? 3 : (r == 12 || r == 18) ? 5 : 0; }
+__host__ __device__ constexpr int trit_tail_bits(int n) { return n == 0 ? 0 : n == 1 ? 2 : n == 2 ? 4 : n == 3 ? 5 : 7; }
+__host__ __device__ constexpr int quint_tail_bits(int n) { return n == 0 ? 0 : n == 1 ? 3 : 5; }
+
+template <int M> struct MD : MI<M> {
+    using I = MI<M>;
+    static constexpr int NC = I::fmt == FMT_RGB ? 3 : I::fmt == FMT_RGBA ? 4 : 2;   // uastc.rs:470
+    static constexpr int N = NC * I::subsets * 2;                                   // uastc.rs:478
+    static constexpr int B = range_bits(I::range);
+    static constexpr int TQ = range_tq(I::range);
+    static constexpr int TQBITS = TQ == 3 ? (N / 5) * 8 + trit_tail_bits(N % 5)
+                                : TQ == 5 ? (N / 3) * 7 + quint_tail_bits(N % 3) : 0;
+    static constexpr int CSB = (I::planes == 2 && I::fmt != FMT_LA) ? 2 : 0;        // uastc.rs:343
+    static constexpr int PB = (M == 7 || I::subsets == 2) ? 5 : I::subsets == 3 ? 4 : 0;   // uastc.rs:352
+    static constexpr int PCOUNT = M == 7 ? 19 : I::subsets == 2 ? 30 : I::subsets == 3 ? 11 : 1;
+    static constexpr int FPOS = I::code_size;                      // transcoding flags
+    static constexpr int CPOS = I::code_size + I::flags_bits;      // component selector
+    static constexpr int PPOS = CPOS + CSB;                        // pattern index
+    static constexpr int EPOS = PPOS + PB;                         // trit / quint groups
+    static constexpr int BPOS = EPOS + TQBITS;                     // raw endpoint bits
+    static constexpr int WPOS = BPOS + N * B;                      // weights
+    static constexpr int WTOT = 16 * I::planes * I::wbits - I::subsets * I::planes;
+    static constexpr int WUNI = 16 * I::planes * I::wbits;         // after re-inserting the anchor MSBs
+    static_assert(WPOS + WTOT <= 128, "mode does not fit a block");
+    static constexpr bool HAS_ALPHA = I::fmt != FMT_RGB;
+};
+
+// ------------------------------------------------------------------------------------------
+// 128-bit register helpers.  Every position is a compile-time constant after inlining, so the
+// selects below fold to nothing; they also stay correct for run-time positions.
+// ------------------------------------------------------------------------------------------
+B2BU_DI uint32_t wsel(const uint4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : i == 3 ? v.w : 0u; }
+
+B2BU_DI uint32_t mask_lo(int n) { return n >= 32 ? 0xFFFFFFFFu : n <= 0 ? 0u : ((1u << n) - 1u); }
+
+// bits [pos, pos+len) of v, len <= 32; bits past 127 read as zero (bitreader.rs:37-60)
+B2BU_DI uint32_t getbits(const uint4& v, int pos, int len)
+{
+    if (len <= 0) return 0u;
+    const int w = pos >> 5, s = pos & 31;
+    const uint32_t lo = wsel(v, w), hi = wsel(v, w + 1);
+    const uint32_t r = (s == 0) ? lo : (s + len <= 32) ? (lo >> s) : __funnelshift_r(lo, hi, s);
+    return (len >= 32 || s + len == 32) ? r : (r & mask_lo(len));
+}
+
+B2BU_DI uint4 shr128(const uint4& v, int k)
+{
+    const int q = k >> 5, r = k & 31;
+    uint4 o;
+    o.x = r ? __funnelshift_r(wsel(v, q), wsel(v, q + 1), r) : wsel(v, q);
+    o.y = r ? __funnelshift_r(wsel(v, q + 1), wsel(v, q + 2), r) : wsel(v, q + 1);
+    o.z = r ? __funnelshift_r(wsel(v, q + 2), wsel(v, q + 3), r) : wsel(v, q + 2);
+    o.w = r ? (wsel(v, q + 3) >> r) : wsel(v, q + 3);
+    return o;
+}
+B2BU_DI uint4 shl128(const uint4& v, int k)
+{
+    const int q = k >> 5, r = k & 31;
+    uint4 o;
+    o.w = r ? __funnelshift_l(wsel(v, 2 - q), wsel(v, 3 - q), r) : wsel(v, 3 - q);
+    o.z = r ? __funnelshift_l(wsel(v, 1 - q), wsel(v, 2 - q), r) : wsel(v, 2 - q);
+    o.y = r ? __funnelshift_l(wsel(v, 0 - q), wsel(v, 1 - q), r) : wsel(v, 1 - q);
+    o.x = r ? (wsel(v, 0 - q) << r) : wsel(v, 0 - q);
+    return o;
+}
+B2BU_DI uint4 or128(const uint4& a, const uint4& b) { return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
+B2BU_DI uint4 xor128(const uint4& a, const uint4& b) { return make_uint4(a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w); }
+B2BU_DI uint4 and128(const uint4& a, const uint4& b) { return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w); }
+// low n bits set
+B2BU_DI uint4 mask128(int n)
+{
+    return make_uint4(mask_lo(n), mask_lo(n - 32), mask_lo(n - 64), mask_lo(n - 96));
+}
+B2BU_DI uint4 u64_to_128(uint64_t v) { return make_uint4((uint32_t)v, (uint32_t)(v >> 32), 0u, 0u); }
+B2BU_DI uint4 u32_to_128(uint32_t v) { return make_uint4(v, 0u, 0u, 0u); }
+
+// OR `len` (<= 32) bits of val into out at bit position pos (bitwriter.rs:23-51, overflow dropped)
+B2BU_DI void putbits(uint4& out, int pos, int len, uint32_t val)
+{
+    if (len <= 0) return;
+    out = or128(out, shl128(u32_to_128(val & mask_lo(len)), pos));
+}
+
+// zero bit inserted at position pos: bits >= pos move up by one
+template <typename T> B2BU_DI T insert_zero(T v, uint32_t pos)
+{
+    const T low = v & (((T)1 << pos) - (T)1);
+    return low | ((v ^ low) << 1);
+}
+// bit at position pos removed: bits > pos move down by one
+template <typename T> B2BU_DI T delete_bit(T v, uint32_t pos)
+{
+    const T low = v & (((T)1 << pos) - (T)1);
+    return low | ((v >> (pos + 1)) << pos);
+}
+
+// ------------------------------------------------------------------------------------------
+// Front-end: header fields, endpoints, weights
+// ------------------------------------------------------------------------------------------
+template <int M> B2BU_DI uint32_t read_compsel(const uint4& b)                 // uastc.rs:343-350
+{
+    using D = MD<M>;
+    if (D::CSB) return getbits(b, D::CPOS, 2);
+    return D::planes == 2 ? 3u : 0u;
+}
+template <int M> B2BU_DI uint32_t read_pattern(const uint4& b) { return getbits(b, MD<M>::PPOS, MD<M>::PB); }
+
+template <int M> B2BU_DI uint32_t pattern_word(const DevTables& T, uint32_t pat)          // uastc.rs:368-376
+{
+    if (M == 7) return T.pat23[pat];
+    if (MD<M>::subsets == 2) return T.pat2[pat];
+    if (MD<M>::subsets == 3) return T.pat3[pat];
+    return 0u;
+}
+template <int M> B2BU_DI uint32_t anchor_byte(const DevTables& T, uint32_t pat)            // uastc.rs:378-385
+{
+    if (M == 7) return T.anc23[pat];
+    if (MD<M>::subsets == 2) return T.anc2[pat];
+    if (MD<M>::subsets == 3) return T.anc3[pat];
+    return 0u;
+}
+
+// uastc.rs:616-695 decode_endpoints: digits (trit/quint) and raw bits per value
+template <int M> B2BU_DI void unpack_quant(const uint4& b, const DevTables& T, uint32_t (&m)[MD<M>::N], uint32_t (&d)[MD<M>::N])
+{
+    using D = MD<M>;
+    if (D::TQ == 3) {
+#pragma unroll
+        for (int g = 0; g < (D::N + 4) / 5; g++) {
+            const int cnt = (D::N - 5 * g) < 5 ? (D::N - 5 * g) : 5;
+            const int nb = cnt == 5 ? 8 : trit_tail_bits(cnt);
+            const uint32_t x = T.trit_dec[getbits(b, D::EPOS + 8 * g, nb)];
+#pragma unroll
+            for (int k = 0; k < cnt; k++) d[5 * g + k] = (x >> (2 * k)) & 3u;
+        }
+    } else if (D::TQ == 5) {
+#pragma unroll
+        for (int g = 0; g < (D::N + 2) / 3; g++) {
+            const int cnt = (D::N - 3 * g) < 3 ? (D::N - 3 * g) : 3;
+            const int nb = cnt == 3 ? 7 : quint_tail_bits(cnt);
+            const uint32_t x = T.quint_dec[getbits(b, D::EPOS + 7 * g, nb)];
+#pragma unroll
+            for (int k = 0; k < cnt; k++) d[3 * g + k] = (x >> (3 * k)) & 7u;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < D::N; i++) d[i] = 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < D::N; i++) m[i] = getbits(b, D::BPOS + D::B * i, D::B);
+}
+
+// uastc.rs:585-614 unquant_endpoint
+template <int M> B2BU_DI uint32_t unquant(const DevTables& T, uint32_t d, uint32_t m)
+{
+    constexpr int R = MD<M>::range;
+    if (R == 20) return m;
+    if (R == 8) return m * 17u;
+    if (R == 11) return (m << 3) | (m >> 2);
+    const uint32_t idx = (d << MD<M>::B) | m;
+    if (R == 7) return T.unq7[idx];
+    if (R == 12) return T.unq12[idx];
+    if (R == 13) return T.unq13[idx];
+    if (R == 18) return T.unq18[idx];
+    return T.unq19[idx];
+}
+
+// uastc.rs:721-740 decode_weights, returned as ONE uniform LSB-first stream: 16*planes fields of
+// wbits bits (texel-major, plane-minor) with the anchors' missing MSB re-inserted as zero.
+template <int M> B2BU_DI uint4 uniform_weights(const uint4& b, const DevTables& T, uint32_t pat)
+{
+    using D = MD<M>;
+    constexpr int wb = D::wbits;
+    uint4 R = and128(shr128(b, D::WPOS), mask128(D::WTOT));
+    if (D::subsets == 1) {
+        if (D::planes == 1) {
+            const uint4 low = and128(R, mask128(wb - 1));
+            return or128(low, shl128(shr128(R, wb - 1), wb));
+        } else {
+            const uint4 f0 = and128(R, mask128(wb - 1));
+            const uint4 f1 = shl128(and128(shr128(R, wb - 1), mask128(wb - 1)), wb);
+            return or128(or128(f0, f1), shl128(shr128(R, 2 * wb - 2), 2 * wb));
+        }
+    } else {
+        const uint32_t ab = anchor_byte<M>(T, pat);
+        const uint32_t a1 = ab & 15u, a2 = ab >> 4;
+        if (D::WUNI <= 32) {
+            uint32_t v = R.x;
+            v = insert_zero<uint32_t>(v, wb - 1);
+            v = insert_zero<uint32_t>(v, a1 * wb + wb - 1);
+            if (D::subsets == 3) v = insert_zero<uint32_t>(v, a2 * wb + wb - 1);
+            return u32_to_128(v);
+        } else {
+            uint64_t v = (uint64_t)R.x | ((uint64_t)R.y << 32);
+            v = insert_zero<uint64_t>(v, wb - 1);
+            v = insert_zero<uint64_t>(v, a1 * wb + wb - 1);
+            if (D::subsets == 3) v = insert_zero<uint64_t>(v, a2 * wb + wb - 1);
+            return u64_to_128(v);
+        }
+    }
+}
+
+// uastc.rs:697-719 unquant_weights: ASTC rule = replicate to 6 bits, +1 above 32
+template <int WB> B2BU_DI uint32_t unquant_weight(uint32_t w)
+{
+    uint32_t r;
+    if (WB == 1) r = w * 63u;
+    else if (WB == 2) r = w * 21u;
+    else if (WB == 3) r = w * 9u;
+    else if (WB == 4) r = (w << 2) | (w >> 2);
+    else r = (w << 1) | (w >> 4);
+    return r + (r >> 5);
+}
+
+// Two 8-bit channels in 16-bit lanes: ((l*257)*(64-w) + (h*257)*w + 32) >> 14 per lane
+// (uastc.rs:218-235 with srgb=false), using floor((257t+32)/2^14) == (t + ((t+32)>>8)) >> 6.
+B2BU_DI uint32_t lerp2(uint32_t lo, uint32_t hi, uint32_t w)
+{
+    const uint32_t t = lo * (64u - w) + hi * w;
+    const uint32_t u = t + (((t + 0x00200020u) >> 8) & 0x00FF00FFu);
+    return (u >> 6) & 0x00FF00FFu;
+}
+
+// Unquantised endpoints as packed pairs per subset: rb = R | B << 16, ga = G | A << 16 (uastc.rs:176-216)
+template <int M> struct Pairs { uint32_t lo_rb[MD<M>::subsets], hi_rb[MD<M>::subsets], lo_ga[MD<M>::subsets], hi_ga[MD<M>::subsets]; };
+
+template <int M> B2BU_DI void assemble_pairs(const uint32_t (&e)[MD<M>::N], Pairs<M>& p)
+{
+    using D = MD<M>;
+#pragma unroll
+    for (int s = 0; s < D::subsets; s++) {
+        const int o = s * D::NC * 2;
+        if (D::fmt == FMT_RGB) {
+            p.lo_rb[s] = e[o + 0] | (e[o + 4] << 16); p.hi_rb[s] = e[o + 1] | (e[o + 5] << 16);
+            p.lo_ga[s] = e[o + 2] | 0x00FF0000u;      p.hi_ga[s] = e[o + 3] | 0x00FF0000u;
+        } else if (D::fmt == FMT_RGBA) {
+            p.lo_rb[s] = e[o + 0] | (e[o + 4] << 16); p.hi_rb[s] = e[o + 1] | (e[o + 5] << 16);
+            p.lo_ga[s] = e[o + 2] | (e[o + 6] << 16); p.hi_ga[s] = e[o + 3] | (e[o + 7] << 16);
+        } else {
+            p.lo_rb[s] = e[o + 0] * 0x00010001u;      p.hi_rb[s] = e[o + 1] * 0x00010001u;
+            p.lo_ga[s] = e[o + 0] | (e[o + 2] << 16); p.hi_ga[s] = e[o + 1] | (e[o + 3] << 16);
+        }
+    }
+}
+
+template <int M> B2BU_DI void unpack_endpoints(const uint4& b, const DevTables& T, uint32_t (&e)[MD<M>::N])
+{
+    uint32_t m[MD<M>::N], d[MD<M>::N];
+    unpack_quant<M>(b, T, m, d);
+#pragma unroll
+    for (int i = 0; i < MD<M>::N; i++) e[i] = unquant<M>(T, d[i], m[i]);
+}
+
+// uastc.rs:237-327 decode_block_to_rgba for one (non void-extent) mode; px = 0xAABBGGRR, raster order
+template <int M> B2BU_DI void decode_rgba(const uint4& b, const DevTables& T, uint32_t pat, uint32_t compsel, uint32_t (&px)[16])
+{
+    using D = MD<M>;
+    uint32_t e[D::N];
+    unpack_endpoints<M>(b, T, e);
+    Pairs<M> p;
+    assemble_pairs<M>(e, p);
+    const uint4 U = uniform_weights<M>(b, T, pat);
+    const uint32_t pw = pattern_word<M>(T, pat);
+    uint32_t mrb = 0u, mga = 0u;
+    if (D::planes == 2) {
+        mrb = compsel == 0u ? 0x000000FFu : compsel == 2u ? 0x00FF0000u : 0u;
+        mga = compsel == 1u ? 0x000000FFu : compsel == 3u ? 0x00FF0000u : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        uint32_t lrb = p.lo_rb[0], hrb = p.hi_rb[0], lga = p.lo_ga[0], hga = p.hi_ga[0];
+        if (D::subsets >= 2) {
+            const uint32_t s = (pw >> (2 * i)) & 3u;
+            if (s == 1u) { lrb = p.lo_rb[1]; hrb = p.hi_rb[1]; lga = p.lo_ga[1]; hga = p.hi_ga[1]; }
+            if (D::subsets == 3) if (s == 2u) { lrb = p.lo_rb[D::subsets - 1]; hrb = p.hi_rb[D::subsets - 1]; lga = p.lo_ga[D::subsets - 1]; hga = p.hi_ga[D::subsets - 1]; }
+        }
+        const uint32_t w0 = unquant_weight<D::wbits>(getbits(U, i * D::planes * D::wbits, D::wbits));
+        uint32_t rb = lerp2(lrb, hrb, w0), ga = lerp2(lga, hga, w0);
+        if (D::planes == 2) {
+            const uint32_t w1 = unquant_weight<D::wbits>(getbits(U, (i * 2 + 1) * D::wbits, D::wbits));
+            const uint32_t rb1 = lerp2(lrb, hrb, w1), ga1 = lerp2(lga, hga, w1);
+            rb = (rb & ~mrb) | (rb1 & mrb);
+            ga = (ga & ~mga) | (ga1 & mga);
+        }
+        px[i] = rb | (ga << 8);
+    }
+}
+
+// void-extent colour (uastc.rs:387-394): bits 5..36
+B2BU_DI uint32_t mode8_rgba(const uint4& b) { return getbits(b, 5, 32); }
+
+// ------------------------------------------------------------------------------------------
+// ASTC back-end (target_formats/astc.rs:8-181)
+// ------------------------------------------------------------------------------------------
+B2BU_DI uint4 astc_void_extent(uint32_t rgba)                                   // astc.rs:17-43
+{
+    const uint32_t r = rgba & 0xFFu, g = (rgba >> 8) & 0xFFu, bl = (rgba >> 16) & 0xFFu, a = rgba >> 24;
+    return make_uint4(0xFFFFFDFCu, 0xFFFFFFFFu, (r * 257u) | ((g * 257u) << 16), (bl * 257u) | ((a * 257u) << 16));
+}
+
+__host__ __device__ constexpr uint32_t astc_block_mode(int m)                                       // astc.rs:333-354
+{
+    return m == 0 ? 0x0242 : m == 1 ? 0x0042 : m == 2 ? 0x0853 : m == 3 ? 0x1042 : m == 4 ? 0x0842 : m == 5 ? 0x0053
+         : m == 6 ? 0x0442 : m == 7 ? 0x0842 : m == 9 ? 0x0842 : m == 10 ? 0x0242 : m == 11 ? 0x0442 : m == 12 ? 0x0053
+         : m == 13 ? 0x0441 : m == 14 ? 0x0042 : m == 15 ? 0x0242 : m == 16 ? 0x0842 : m == 17 ? 0x0442 : m == 18 ? 0x0253 : 0;
+}
+
+// mask with wbits ones at every texel of `subset` in a 2-bit-per-texel map
+template <int WB> B2BU_DI uint64_t subset_field_mask(uint32_t pw, uint32_t subset)
+{
+    uint64_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        if (((pw >> (2 * i)) & 3u) == subset) m |= (uint64_t)((1u << WB) - 1u) << (WB * i);
+    return m;
+}
+
+template <int M> B2BU_DI uint4 astc_block(const uint4& b, const DevTables& T, uint32_t pat, uint32_t compsel)
+{
+    using D = MD<M>;
+    uint32_t m[D::N], d[D::N];
+    unpack_quant<M>(b, T, m, d);
+
+    // astc.rs:55-78: avoid blue contraction -- swap each endpoint pair of a subset whose first
+    // endpoint has the larger R+G+B, and invert that subset's weights
+    bool inv[3] = {false, false, false};
+    if (D::fmt != FMT_LA) {
+#pragma unroll
+        for (int s = 0; s < D::subsets; s++) {
+            const int o = s * D::NC * 2;
+            const uint32_t s0 = unquant<M>(T, d[o + 0], m[o + 0]) + unquant<M>(T, d[o + 2], m[o + 2]) + unquant<M>(T, d[o + 4], m[o + 4]);
+            const uint32_t s1 = unquant<M>(T, d[o + 1], m[o + 1]) + unquant<M>(T, d[o + 3], m[o + 3]) + unquant<M>(T, d[o + 5], m[o + 5]);
+            inv[s] = s0 > s1;
+#pragma unroll
+            for (int c = 0; c < D::NC; c++) {
+                const uint32_t ma = m[o + 2 * c], mb = m[o + 2 * c + 1], da = d[o + 2 * c], db = d[o + 2 * c + 1];
+                m[o + 2 * c] = inv[s] ? mb : ma; m[o + 2 * c + 1] = inv[s] ? ma : mb;
+                d[o + 2 * c] = inv[s] ? db : da; d[o + 2 * c + 1] = inv[s] ? da : db;
+            }
+        }
+    }
+
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    int pos = 0;
+    // astc.rs:80-96: block mode, partition seed + "same CEM" bits, CEM
+    constexpr uint32_t cem = D::fmt == FMT_RGB ? 8u : D::fmt == FMT_RGBA ? 12u : 4u;
+    uint32_t hdr = astc_block_mode(M);
+    pos = 13;
+    if (D::PB) {
+        const uint32_t seed = M == 7 ? T.seed23[pat] : D::subsets == 2 ? T.seed2[pat] : T.seed3[pat];
+        hdr |= seed << 13;
+        pos += 12;
+    }
+    hdr |= cem << pos;
+    pos += 4;
+    out.x = hdr;
+
+    // astc.rs:98-141: BISE stream, raw bits interleaved with the T / Q bits
+    if (D::TQ == 5) {
+#pragma unroll
+        for (int g = 0; g < (D::N + 2) / 3; g++) {
+            const int cnt = (D::N - 3 * g) < 3 ? (D::N - 3 * g) : 3;
+            uint32_t id = 0;
+#pragma unroll
+            for (int k = cnt - 1; k >= 0; k--) id = id * 5u + d[3 * g + k];
+            const uint32_t q = T.quint_enc[id];
+            // 3B + 7 <= 22 bits per group
+            uint32_t grp = m[3 * g] | ((q & 7u) << D::B);
+            if (cnt > 1) grp |= m[3 * g + 1] << (D::B + 3);
+            grp |= ((q >> 3) & 3u) << (2 * D::B + 3);
+            if (cnt > 2) grp |= m[3 * g + 2] << (2 * D::B + 5);
+            grp |= ((q >> 5) & 3u) << (3 * D::B + 5);
+            putbits(out, pos, 3 * D::B + 7, grp);
+            pos += 3 * D::B + 7;
+        }
+    } else if (D::TQ == 3) {
+#pragma unroll
+        for (int g = 0; g < (D::N + 4) / 5; g++) {
+            const int cnt = (D::N - 5 * g) < 5 ? (D::N - 5 * g) : 5;
+            uint32_t id = 0;
+#pragma unroll
+            for (int k = cnt - 1; k >= 0; k--) id = id * 3u + d[5 * g + k];
+            const uint32_t t = T.trit_enc[id];
+            // 5B + 8 <= 38 bits per group
+            uint64_t grp = (uint64_t)m[5 * g] | ((uint64_t)(t & 3u) << D::B);
+            if (cnt > 1) grp |= (uint64_t)m[5 * g + 1] << (D::B + 2);
+            grp |= (uint64_t)((t >> 2) & 3u) << (2 * D::B + 2);
+            if (cnt > 2) grp |= (uint64_t)m[5 * g + 2] << (2 * D::B + 4);
+            grp |= (uint64_t)((t >> 4) & 1u) << (3 * D::B + 4);
+            if (cnt > 3) grp |= (uint64_t)m[5 * g + 3] << (3 * D::B + 5);
+            grp |= (uint64_t)((t >> 5) & 3u) << (4 * D::B + 5);
+            if (cnt > 4) grp |= (uint64_t)m[5 * g + 4] << (4 * D::B + 7);
+            grp |= (uint64_t)((t >> 7) & 1u) << (5 * D::B + 7);
+            out = or128(out, shl128(u64_to_128(grp), pos));
+            pos += 5 * D::B + 8;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < D::N; i++) { putbits(out, pos, D::B, m[i]); pos += D::B; }
+    }
+
+    // astc.rs:143-178: weights fill from bit 127 downward, each bit-reversed == the uniform
+    // LSB-first stream reversed as a whole; CCS follows un-reversed
+    uint4 U = uniform_weights<M>(b, T, pat);
+    if (D::subsets == 1) {
+        if (inv[0]) U = xor128(U, mask128(D::WUNI));
+    } else {
+        const uint32_t pw = pattern_word<M>(T, pat);
+        uint64_t x = 0;
+#pragma unroll
+        for (int s = 0; s < D::subsets; s++)
+            if (inv[s]) x |= subset_field_mask<D::wbits>(pw, s);
+        U = xor128(U, u64_to_128(x));
+    }
+    const uint4 Wrev = make_uint4(__brev(U.w), __brev(U.z), __brev(U.y), __brev(U.x));
+    out = or128(out, Wrev);
+    if (D::planes == 2) putbits(out, 128 - D::WUNI - 2, 2, compsel);
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------
+// BC7 back-end (target_formats/bc7.rs:9-553)
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int bc7_mode_for(int m)                                               // bc7.rs:582-589
+{
+    return m == 0 ? 6 : m == 1 ? 3 : m == 2 ? 1 : m == 3 ? 2 : m == 4 ? 3 : m == 5 ? 6 : m == 6 ? 5 : m == 7 ? 2
+         : m == 9 ? 7 : m == 10 ? 6 : m == 11 ? 5 : m == 12 ? 6 : m == 13 ? 5 : m == 14 ? 6 : m == 15 ? 6 : m == 16 ? 7
+         : m == 17 ? 5 : 6;
+}
+struct Bc7Info { int pat_bits, color_bits, alpha_bits, weight_bits, planes, subsets, p_bits, sp_bits, channels; };
+__host__ __device__ constexpr Bc7Info bc7_info(int bm)                                              // bc7.rs:570-579
+{
+    return bm == 1 ? Bc7Info{6, 6, 0, 3, 1, 2, 0, 1, 3} : bm == 2 ? Bc7Info{6, 5, 0, 2, 1, 3, 0, 0, 3}
+         : bm == 3 ? Bc7Info{6, 7, 0, 2, 1, 2, 1, 0, 3} : bm == 5 ? Bc7Info{0, 7, 8, 2, 2, 1, 0, 0, 4}
+         : bm == 6 ? Bc7Info{0, 7, 7, 4, 1, 1, 1, 0, 4} : Bc7Info{6, 5, 5, 2, 1, 2, 1, 0, 4};
+}
+
+// bc7.rs:312-375 + :18-59: void-extent -> BC7 mode 6 (lossless unless a channel is 0 and another 255) or mode 5
+B2BU_DI uint4 bc7_void_extent(uint32_t rgba, const DevTables& T)
+{
+    uint32_t c[4] = {rgba & 0xFFu, (rgba >> 8) & 0xFFu, (rgba >> 16) & 0xFFu, rgba >> 24};
+    uint32_t err0 = 0, err1 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { err0 += c[i] == 255u; err1 += c[i] == 0u; }
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    if (err0 > 0 && err1 > 0) {
+        // mode 5: 6 mode bits, 2 rotation bits, 7-bit colour pairs, 8-bit alpha pair, colour index 1, alpha index 0
+        int pos = 8;
+        out.x = 1u << 5;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { putbits(out, pos, 7, T.m5lo[c[i]]); pos += 7; putbits(out, pos, 7, T.m5hi[c[i]]); pos += 7; }
+        putbits(out, pos, 8, c[3]); pos += 8; putbits(out, pos, 8, c[3]); pos += 8;
+        // colour weights: anchor 1 bit (value 1), then 15 x 2 bits of 01
+        putbits(out, pos, 1, 1u); pos += 1;
+        putbits(out, pos, 30, 0x15555555u); pos += 30;
+        return out;
+    }
+    const uint32_t p = err1 < err0 ? 1u : 0u;
+    int pos = 7;
+    out.x = 1u << 6;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t idx = c[i] + (p ? 0u : 1u);                               // bc7.rs:1126-1131
+        putbits(out, pos, 7, T.m6lo[idx]); pos += 7; putbits(out, pos, 7, T.m6hi[idx]); pos += 7;
+    }
+    putbits(out, pos, 2, p * 3u); pos += 2;
+    // weights: anchor 3 bits (5), then 15 x 4 bits of 5
+    putbits(out, pos, 3, 5u); pos += 3;
+    putbits(out, pos, 32, 0x55555555u); pos += 32;
+    putbits(out, pos, 28, 0x05555555u);
+    return out;
+}
+
+// bc7.rs:478-553 determine_unique_pbits for 8 total bits (BC7 modes 3 and 6), integer form:
+// quantise(v,p) = nearest value of parity p (ties up), clamp; error = [parity(v) != p]
+B2BU_DI uint32_t q8(uint32_t v, uint32_t p)
+{
+    // ((v - p + 1) >> 1) * 2 + p clamped to [p, 254 + p]
+    const uint32_t q = (((v + 1u - p) >> 1) << 1) + p;
+    return q > 254u + p ? 254u + p : q;
+}
+
+template <int M> B2BU_DI uint4 bc7_block(const uint4& b, const DevTables& T, uint32_t pat, uint32_t compsel)
+{
+    using D = MD<M>;
+    constexpr int BM = bc7_mode_for(M);
+    constexpr Bc7Info BI = bc7_info(BM);
+    constexpr int bb = BI.weight_bits;
+
+    uint32_t e[D::N];
+    unpack_endpoints<M>(b, T, e);
+    // endpoint pairs per UASTC subset, channels R,G,B,A (uastc.rs:176-216)
+    uint32_t lo[3][4], hi[3][4];
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) { lo[s][c] = c == 3 ? 255u : 0u; hi[s][c] = c == 3 ? 255u : 0u; }
+    }
+#pragma unroll
+    for (int s = 0; s < D::subsets; s++) {
+        const int o = s * D::NC * 2;
+        if (D::fmt == FMT_LA) {
+            lo[s][0] = lo[s][1] = lo[s][2] = e[o]; hi[s][0] = hi[s][1] = hi[s][2] = e[o + 1];
+            lo[s][3] = e[o + 2]; hi[s][3] = e[o + 3];
+        } else {
+#pragma unroll
+            for (int c = 0; c < D::NC; c++) { lo[s][c] = e[o + 2 * c]; hi[s][c] = e[o + 2 * c + 1]; }
+        }
+    }
+
+    // weights per plane, converted to the BC7 width (bc7.rs:377-398)
+    const uint4 U = uniform_weights<M>(b, T, pat);
+    uint32_t w[2][16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+#pragma unroll
+        for (int p = 0; p < D::planes; p++) {
+            uint32_t x = getbits(U, (i * D::planes + p) * D::wbits, D::wbits);
+            if (D::wbits == 1 && bb == 2) x = x * 3u;
+            else if (D::wbits == 2 && bb == 4) x = x * 5u;
+            else if (D::wbits == 3 && bb == 4) x = 2u * x + (x >> 2);
+            else if (D::wbits == 5 && bb == 4) x = T.w5to4[x];
+            w[p][i] = x;
+        }
+    }
+
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    int pos = BM + 1;
+    out.x = 1u << BM;
+
+    uint32_t a1 = 0, a2 = 0;          // BC7 anchors of subsets 1, 2
+    // BC7-side endpoints per BC7 subset
+    uint32_t elo[3][4], ehi[3][4];
+    if (BI.subsets > 1) {
+        // bc7.rs:113-198: partition index, subset permutation, anchor-MSB fix-up
+        uint32_t info, bpw;
+        if (M == 1) { info = 0u | (0u << 8) | (15u << 16) | (2u << 24); bpw = T.bc7pat2[0]; }
+        else if (M == 7) { info = T.bc7p23[pat]; bpw = T.bc7pat23[pat]; }
+        else if (D::subsets == 2) { info = T.bc7p2[pat]; bpw = T.bc7pat2[pat]; }
+        else { info = T.bc7p3[pat]; bpw = T.bc7pat3[pat]; }
+        putbits(out, pos, BI.pat_bits, info & 63u);
+        pos += BI.pat_bits;
+        a1 = (info >> 16) & 15u; a2 = (info >> 20) & 15u;
+#pragma unroll
+        for (int s = 0; s < BI.subsets; s++) {
+            const uint32_t src = (info >> (8 + 2 * s)) & 3u;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t l = lo[0][c], h = hi[0][c];
+                if (D::subsets >= 2) { if (src == 1u) { l = lo[1][c]; h = hi[1][c]; } }
+                if (D::subsets >= 3) { if (src == 2u) { l = lo[2][c]; h = hi[2][c]; } }
+                elo[s][c] = l; ehi[s][c] = h;
+            }
+        }
+        // which BC7 subsets have an anchor weight with its MSB set
+        bool invs[3];
+        uint32_t wa0 = w[0][0], wa1 = 0, wa2 = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) { if ((uint32_t)i == a1) wa1 = w[0][i]; if ((uint32_t)i == a2) wa2 = w[0][i]; }
+        invs[0] = (wa0 >> (bb - 1)) & 1u; invs[1] = (wa1 >> (bb - 1)) & 1u; invs[2] = BI.subsets == 3 ? ((wa2 >> (bb - 1)) & 1u) : false;
+#pragma unroll
+        for (int s = 0; s < BI.subsets; s++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t l = elo[s][c], h = ehi[s][c];
+                elo[s][c] = invs[s] ? h : l; ehi[s][c] = invs[s] ? l : h;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const uint32_t s = (bpw >> (2 * i)) & 3u;
+            const bool iv = s == 0u ? invs[0] : s == 1u ? invs[1] : invs[2];
+            if (iv) w[0][i] = (~w[0][i]) & ((1u << bb) - 1u);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; c++) { elo[0][c] = lo[0][c]; ehi[0][c] = hi[0][c]; }
+        if (D::planes == 2) {
+            // bc7.rs:207-246: rotate the dual-plane channel into alpha.  The "anchor MSB set" branches
+            // (:200-205, :208-236) are dead: UASTC anchors carry no MSB and every width LUT keeps them low.
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const uint32_t l = elo[0][c], h = ehi[0][c];
+                const bool sw = compsel == (uint32_t)c;
+                elo[0][c] = sw ? elo[0][3] : l; ehi[0][c] = sw ? ehi[0][3] : h;
+                elo[0][3] = sw ? l : elo[0][3]; ehi[0][3] = sw ? h : ehi[0][3];
+            }
+            putbits(out, pos, 2, (compsel + 1u) & 3u);
+            pos += 2;
+        }
+    }
+
+    // endpoint re-quantisation (bc7.rs:249-273)
+    uint32_t pb[3][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}};
+    if (BI.p_bits) {
+#pragma unroll
+        for (int s = 0; s < BI.subsets; s++) {
+            if (BI.color_bits == 7) {
+                // 8 total bits: error of p is the number of channels whose parity differs from p
+                uint32_t odd_l = 0, odd_h = 0;
+#pragma unroll
+                for (int c = 0; c < BI.channels; c++) { odd_l += elo[s][c] & 1u; odd_h += ehi[s][c] & 1u; }
+                // err0 = #odd (+ v==255 counts as odd already), err1 = #even; p=1 iff err1 < err0
+                const uint32_t pl = (BI.channels - odd_l) < odd_l ? 1u : 0u;
+                const uint32_t ph = (BI.channels - odd_h) < odd_h ? 1u : 0u;
+#pragma unroll
+                for (int c = 0; c < 4; c++) { elo[s][c] = q8(elo[s][c], pl) >> 1; ehi[s][c] = q8(ehi[s][c], ph) >> 1; }
+                pb[s][0] = pl; pb[s][1] = ph;
+            } else {
+                // 6 total bits (BC7 mode 7): LUT of quantised value and exact squared error
+                uint32_t el0 = 0, el1 = 0, eh0 = 0, eh1 = 0;
+#pragma unroll
+                for (int c = 0; c < BI.channels; c++) {
+                    el0 += T.pe6[0][elo[s][c]]; el1 += T.pe6[1][elo[s][c]];
+                    eh0 += T.pe6[0][ehi[s][c]]; eh1 += T.pe6[1][ehi[s][c]];
+                }
+                const uint32_t pl = el1 < el0 ? 1u : 0u, ph = eh1 < eh0 ? 1u : 0u;
+#pragma unroll
+                for (int c = 0; c < 4; c++) { elo[s][c] = T.pq6[pl][elo[s][c]] >> 1; ehi[s][c] = T.pq6[ph][ehi[s][c]] >> 1; }
+                pb[s][0] = pl; pb[s][1] = ph;
+            }
+        }
+    } else if (BI.sp_bits) {
+        // BC7 mode 1 <= UASTC mode 2: endpoints are 17*k; f32 terms from the LUT, summed in the reference's order
+#pragma unroll
+        for (int s = 0; s < BI.subsets; s++) {
+            float err[2];
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float t = __fadd_rn(__uint_as_float(T.se7_bits[p][elo[s][c] / 17u]), __uint_as_float(T.se7_bits[p][ehi[s][c] / 17u]));
+                    acc = __fadd_rn(acc, t);
+                }
+                err[p] = acc;
+            }
+            const uint32_t p = err[1] < err[0] ? 1u : 0u;
+#pragma unroll
+            for (int c = 0; c < 3; c++) { elo[s][c] = T.sq7[p][elo[s][c] / 17u] >> 1; ehi[s][c] = T.sq7[p][ehi[s][c] / 17u] >> 1; }
+            pb[s][0] = p; pb[s][1] = p;
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < BI.subsets; s++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t mk = (1u << (c == 3 ? BI.alpha_bits : BI.color_bits)) - 1u;
+                elo[s][c] = (elo[s][c] * mk + 127u) / 255u; ehi[s][c] = (ehi[s][c] * mk + 127u) / 255u;
+            }
+        }
+    }
+
+    // bc7.rs:276-307: endpoints channel-major, p-bits, weights
+#pragma unroll
+    for (int c = 0; c < BI.channels; c++) {
+        const int nb = c == 3 ? BI.alpha_bits : BI.color_bits;
+#pragma unroll
+        for (int s = 0; s < BI.subsets; s++) {
+            putbits(out, pos, nb, elo[s][c]); pos += nb;
+            putbits(out, pos, nb, ehi[s][c]); pos += nb;
+        }
+    }
+    if (BI.p_bits) {
+#pragma unroll
+        for (int s = 0; s < BI.subsets; s++) { putbits(out, pos, 2, (pb[s][1] << 1) | pb[s][0]); pos += 2; }
+    } else if (BI.sp_bits) {
+        putbits(out, pos, 2, (pb[1][0] << 1) | pb[0][0]); pos += 2;
+    }
+    // weights: build the uniform bb-bit stream per plane, then drop the anchors' MSB (always 0 by now)
+#pragma unroll
+    for (int p = 0; p < BI.planes; p++) {
+        uint64_t ws = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) ws |= (uint64_t)w[p][i] << (bb * i);
+        if (BI.subsets == 3) {
+            const uint32_t ahi = a1 > a2 ? a1 : a2, alo = a1 > a2 ? a2 : a1;
+            ws = delete_bit<uint64_t>(ws, ahi * bb + bb - 1);
+            ws = delete_bit<uint64_t>(ws, alo * bb + bb - 1);
+        } else if (BI.subsets == 2) {
+            ws = delete_bit<uint64_t>(ws, a1 * bb + bb - 1);
+        }
+        ws = delete_bit<uint64_t>(ws, bb - 1);
+        out = or128(out, shl128(u64_to_128(ws), pos));
+        pos += 16 * bb - BI.subsets;
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------
+// ETC1 / ETC2 back-end (target_formats/etc.rs:11-341).  Mode independent once the texels exist.
+// ------------------------------------------------------------------------------------------
+struct EtcFlags { uint32_t flip, diff, i0, i1, has_bias, bias, etc2tm; };
+
+template <int M> B2BU_DI EtcFlags read_trans_flags(const uint4& b)             // uastc.rs:411-436
+{
+    using D = MD<M>;
+    constexpr bool m10_12 = (M >= 10 && M <= 12);
+    EtcFlags f;
+    int pos = D::FPOS + 1 + (m10_12 ? 0 : 1);            // bc1h0, bc1h1
+    f.flip = getbits(b, pos, 1); pos += 1;
+    f.diff = getbits(b, pos, 1); pos += 1;
+    f.i0 = getbits(b, pos, 3); pos += 3;
+    f.i1 = getbits(b, pos, 3); pos += 3;
+    f.has_bias = m10_12 ? 0u : 1u;
+    f.bias = m10_12 ? 0u : getbits(b, pos, 5); pos += m10_12 ? 0 : 5;
+    f.etc2tm = D::HAS_ALPHA ? getbits(b, pos, 8) : 0u;
+    return f;
+}
+
+B2BU_DI uint2 etc2_solid_alpha(uint32_t v)                                      // etc.rs:261-275
+{
+    return make_uint2(v | (0x1Du << 8) | (0x92u << 16) | (0x49u << 24), 0x24u | (0x92u << 8) | (0x49u << 16) | (0x24u << 24));
+}
+
+// etc.rs:277-341 write_etc2_alpha_block
+B2BU_DI uint2 etc2_alpha_block(const uint32_t (&px)[16], uint32_t etc2tm, const DevTables& T)
+{
+    if (etc2tm == 0u) return etc2_solid_alpha(255u);
+    uint32_t mn = 255u, mx = 0u;
+#pragma unroll
+    for (int i = 0; i < 16; i++) { const uint32_t a = px[i] >> 24; mn = min(mn, a); mx = max(mx, a); }
+    if (mn == mx) return etc2_solid_alpha(mn);
+    const uint32_t ti = etc2tm & 15u;
+    const int mult = (int)(etc2tm >> 4);
+    // centre = round(lerp(min, max, -mod_min/range)), literal f32 with no contraction (etc.rs:301-307)
+    const float amt = __uint_as_float(T.eac_amt_bits[ti]), om = __uint_as_float(T.eac_1m_amt_bits[ti]);
+    const float l = __fadd_rn(__fmul_rn((float)mn, om), __fmul_rn((float)mx, amt));
+    const int center = (int)roundf(l);
+    int vals[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { const int v = center + (int)T.eac_mod[ti][k] * mult; vals[k] = v < 0 ? 0 : v > 255 ? 255 : v; }
+    uint64_t sel = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int a = (int)(px[i] >> 24);
+        uint32_t best = 0xFFFFFFFFu;                     // (|diff| << 3) | index: min() keeps the first minimum
+#pragma unroll
+        for (int k = 0; k < 8; k++) best = min(best, ((uint32_t)abs(vals[k] - a) << 3) | (uint32_t)k);
+        const int x = i / 4, y = i % 4, id = y * 4 + x;  // etc.rs:325-329 (transposed pixel order)
+        sel |= (uint64_t)(best & 7u) << (45 - id * 3);
+    }
+    // bytes: centre, etc2tm, then selectors big-endian (48 bits)
+    const uint32_t s47_40 = (uint32_t)(sel >> 40) & 0xFFu, s39_32 = (uint32_t)(sel >> 32) & 0xFFu;
+    const uint32_t lo32 = (uint32_t)sel;
+    uint2 r;
+    r.x = ((uint32_t)center & 0xFFu) | (etc2tm << 8) | (s47_40 << 16) | (s39_32 << 24);
+    r.y = __byte_perm(lo32, 0u, 0x0123);
+    return r;
+}
+
+// etc.rs:203-259 apply_etc1_bias for one channel
+B2BU_DI int etc1_bias_delta(uint32_t bias, int c, uint32_t subblock)
+{
+    const bool s1 = subblock == 1u;
+    switch (bias) {
+    case 2:  return s1 ? 0 : (c == 0 ? -1 : 0);
+    case 5:  return s1 ? 0 : (c == 1 ? -1 : 0);
+    case 6:  return s1 ? 0 : (c == 2 ? -1 : 0);
+    case 7:  return s1 ? 0 : (c == 0 ? 1 : 0);
+    case 11: return s1 ? 0 : (c == 1 ? 1 : 0);
+    case 15: return s1 ? 0 : (c == 2 ? 1 : 0);
+    case 18: return s1 ? (c == 0 ? -1 : 0) : 0;
+    case 19: return s1 ? (c == 1 ? -1 : 0) : 0;
+    case 20: return s1 ? (c == 2 ? -1 : 0) : 0;
+    case 21: return s1 ? (c == 0 ? 1 : 0) : 0;
+    case 24: return s1 ? (c == 1 ? 1 : 0) : 0;
+    case 8:  return s1 ? (c == 2 ? 1 : 0) : 0;
+    case 10: return -2;
+    case 27: return s1 ? 0 : -1;
+    case 28: return s1 ? -1 : 1;
+    case 29: return s1 ? 1 : 0;
+    case 30: return s1 ? -1 : 0;
+    case 31: return s1 ? 0 : 1;
+    default: return (int)((bias / (c == 0 ? 1u : c == 1 ? 3u : 9u)) % 3u) - 1;
+    }
+}
+B2BU_DI uint32_t etc1_apply_bias(uint32_t v0, uint32_t bias, int c, uint32_t limit, uint32_t subblock)
+{
+    const int delta = etc1_bias_delta(bias, c, subblock);
+    int v = (int)v0;
+    if (v == 0) v += (delta == -2) ? 3 : delta + 1;
+    else if (v == (int)limit) v += delta - 1;
+    else { v += delta; if (v < 0 || v > (int)limit) v = (v - delta) - delta; }
+    return (uint32_t)v;
+}
+
+// etc.rs:78-198.  The reference transposes the texels when !flip so that each sub-block is a run
+// of 8; here texel (x,y) simply belongs to sub-block (flip ? y>>1 : x>>1) and its selector lands at
+// ETC pixel id x*4+y either way (etc.rs:188-194, :363-393).
+B2BU_DI uint2 etc1_block(const uint32_t (&px)[16], const EtcFlags& f, const DevTables& T)
+{
+    // quadrant sums in 16-bit lanes: q[qy][qx]
+    uint32_t srb[2][2] = {{0u, 0u}, {0u, 0u}}, sg[2][2] = {{0u, 0u}, {0u, 0u}};
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int x = i & 3, y = i >> 2;
+        srb[y >> 1][x >> 1] += px[i] & 0x00FF00FFu;
+        sg[y >> 1][x >> 1] += (px[i] >> 8) & 0xFFu;
+    }
+    const bool flip = f.flip != 0u;
+    // sub-block 0 = TL + (flip ? TR : BL), sub-block 1 = BR + (flip ? BL : TR)
+    const uint32_t rb0 = srb[0][0] + (flip ? srb[0][1] : srb[1][0]), g0 = sg[0][0] + (flip ? sg[0][1] : sg[1][0]);
+    const uint32_t rb1 = srb[1][1] + (flip ? srb[1][0] : srb[0][1]), g1 = sg[1][1] + (flip ? sg[1][0] : sg[0][1]);
+    const uint32_t limit = f.diff ? 31u : 15u;
+    uint32_t c0[3], c1[3];
+    c0[0] = ((rb0 & 0xFFFFu) * limit + 1020u) / 2040u; c0[1] = (g0 * limit + 1020u) / 2040u; c0[2] = ((rb0 >> 16) * limit + 1020u) / 2040u;
+    c1[0] = ((rb1 & 0xFFFFu) * limit + 1020u) / 2040u; c1[1] = (g1 * limit + 1020u) / 2040u; c1[2] = ((rb1 >> 16) * limit + 1020u) / 2040u;
+    if (f.has_bias) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { c0[c] = etc1_apply_bias(c0[c], f.bias, c, limit, 0u); c1[c] = etc1_apply_bias(c1[c], f.bias, c, limit, 1u); }
+    }
+    uint32_t base0[3], base1[3], hdr = 0;
+    if (!f.diff) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            hdr |= ((c0[c] << 4) | c1[c]) << (8 * c);
+            base0[c] = c0[c] * 17u; base1[c] = c1[c] * 17u;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            int dlt = (int)c1[c] - (int)c0[c];
+            dlt = dlt < -4 ? -4 : dlt > 3 ? 3 : dlt;
+            hdr |= ((c0[c] << 3) | ((uint32_t)dlt & 7u)) << (8 * c);
+            const uint32_t c1d = (uint32_t)((int)c0[c] + dlt);
+            base0[c] = (c0[c] << 3) | (c0[c] >> 2); base1[c] = (c1d << 3) | (c1d >> 2);
+        }
+    }
+    hdr |= ((f.i0 << 5) | (f.i1 << 2) | (f.diff << 1) | f.flip) << 24;
+
+    // luminance thresholds per sub-block (etc.rs:165-177)
+    int thr[2][3];
+#pragma unroll
+    for (int sb = 0; sb < 2; sb++) {
+        const uint32_t inten = sb ? f.i1 : f.i0;
+        int lum[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int md = T.etc1_mod[inten][k];
+            int l = 0;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                int v = (int)(sb ? base1[c] : base0[c]) + md;
+                v = v < 0 ? 0 : v > 255 ? 255 : v;
+                l += v * (c == 0 ? 108 : c == 1 ? 366 : 38);
+            }
+            lum[k] = l;
+        }
+        thr[sb][0] = (lum[0] + lum[1]) / 2; thr[sb][1] = (lum[1] + lum[2]) / 2; thr[sb][2] = (lum[2] + lum[3]) / 2;
+    }
+    // thresholds for the two quadrants whose sub-block depends on flip: TR (x>=2,y<2) and BL (x<2,y>=2)
+    int thr_tr[3], thr_bl[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { thr_tr[k] = flip ? thr[0][k] : thr[1][k]; thr_bl[k] = flip ? thr[1][k] : thr[0][k]; }
+
+    uint32_t selbits = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int x = i & 3, y = i >> 2;
+        const int qx = x >> 1, qy = y >> 1;
+        const int t0 = (qx == qy) ? thr[qx][0] : (qx ? thr_tr[0] : thr_bl[0]);
+        const int t1 = (qx == qy) ? thr[qx][1] : (qx ? thr_tr[1] : thr_bl[1]);
+        const int t2 = (qx == qy) ? thr[qx][2] : (qx ? thr_tr[2] : thr_bl[2]);
+        const int lum = (int)(px[i] & 0xFFu) * 108 + (int)((px[i] >> 8) & 0xFFu) * 366 + (int)((px[i] >> 16) & 0xFFu) * 38;
+        const uint32_t sel = (uint32_t)(lum >= t0) + (uint32_t)(lum >= t1) + (uint32_t)(lum >= t2);
+        // selector -> ETC1 code [3,2,0,1]: msb = sel < 2, lsb = (sel == 0 || sel == 3)   (etc.rs:433)
+        const uint32_t msb = sel < 2u ? 1u : 0u, lsb = (sel == 0u || sel == 3u) ? 1u : 0u;
+        const int pid = x * 4 + y;
+        const int bitpos = pid < 8 ? 8 + pid : pid - 8;  // byte 1 holds pixels 0..7, byte 0 pixels 8..15
+        selbits |= (msb << bitpos) | (lsb << (16 + bitpos));
+    }
+    return make_uint2(hdr, selbits);
+}
+
+// etc.rs:43-76: void-extent -> ETC1 from the stored hints
+B2BU_DI uint2 etc1_void_extent(const uint4& b)
+{
+    const uint32_t d = getbits(b, 37, 1), ii = getbits(b, 38, 3), s = getbits(b, 41, 2);
+    const uint32_t r = getbits(b, 43, 5), g = getbits(b, 48, 5), bl = getbits(b, 53, 5);
+    uint32_t hdr;
+    // u8 arithmetic in the reference: (c << 4 | c) keeps only the low 8 bits (etc.rs:54-56)
+    if (!d) hdr = (((r << 4) | r) & 0xFFu) | ((((g << 4) | g) & 0xFFu) << 8) | ((((bl << 4) | bl) & 0xFFu) << 16);
+    else hdr = (r << 3) | (g << 11) | (bl << 19);
+    hdr |= ((ii << 5) | (ii << 2) | (d << 1)) << 24;
+    const uint32_t code = (0x1u << 6 | 0x0u << 4 | 0x2u << 2 | 0x3u) >> (2 * s) & 3u;   // [3,2,0,1][s]
+    const uint32_t hi = (code >> 1) ? 0xFFFFu : 0u, lo = (code & 1u) ? 0xFFFFu : 0u;
+    return make_uint2(hdr, hi | (lo << 16));
+}
+
+// ------------------------------------------------------------------------------------------
+// One block, any mode: dispatch on the mode id to the specialised code above.
+// ------------------------------------------------------------------------------------------
+#define B2BU_FOR_EACH_MODE(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18)
+
+// ---- per-target block functions: return false on error ------------------------------------
+struct BlockOut { uint4 v; uint2 etc; uint32_t px[16]; };
+
+template <int M> B2BU_DI bool header_ok(const uint4& b, uint32_t& pat, uint32_t& compsel)
+{
+    compsel = read_compsel<M>(b);
+    pat = read_pattern<M>(b);
+    return pat < (uint32_t)MD<M>::PCOUNT;          // uastc.rs:360-365
+}
+
+template <int TARGET>
+B2BU_DI uint32_t transcode_one(const uint4& b, const DevTables& T, BlockOut& o)
+{
+    const uint32_t mode = T.mode_lut[b.x & 127u];  // uastc.rs:329-341
+    uint32_t pat = 0, compsel = 0;
+    if (mode == 8u) {
+        const uint32_t c = mode8_rgba(b);
+        if (TARGET == TGT_RGBA) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) o.px[i] = c;
+        } else if (TARGET == TGT_ASTC) o.v = astc_void_extent(c);
+        else if (TARGET == TGT_BC7) o.v = bc7_void_extent(c, T);
+        else {
+            o.etc = etc1_void_extent(b);
+            if (TARGET == TGT_ETC2) { const uint2 a = etc2_solid_alpha(c >> 24); o.v = make_uint4(a.x, a.y, o.etc.x, o.etc.y); }
+        }
+        return ERR_OK;
+    }
+    if (TARGET == TGT_ASTC || TARGET == TGT_BC7) {
+        switch (mode) {
+#define X(M) case M: if (!header_ok<M>(b, pat, compsel)) return ERR_PATTERN; \
+                     o.v = (TARGET == TGT_ASTC) ? astc_block<M>(b, T, pat, compsel) : bc7_block<M>(b, T, pat, compsel); break;
+            B2BU_FOR_EACH_MODE(X)
+#undef X
+        default: return ERR_MODE;
+        }
+        return ERR_OK;
+    }
+    // RGBA, ETC1, ETC2: decode the texels once, then (for ETC) run the mode-independent packer
+    EtcFlags f;
+    switch (mode) {
+#define X(M) case M: if (!header_ok<M>(b, pat, compsel)) return ERR_PATTERN; \
+                     if (TARGET != TGT_RGBA) f = read_trans_flags<M>(b); \
+                     decode_rgba<M>(b, T, pat, compsel, o.px); break;
+        B2BU_FOR_EACH_MODE(X)
+#undef X
+    default: return ERR_MODE;
+    }
+    if (TARGET == TGT_ETC1 || TARGET == TGT_ETC2) {
+        o.etc = etc1_block(o.px, f, T);
+        if (TARGET == TGT_ETC2) { const uint2 a = etc2_alpha_block(o.px, f.etc2tm, T); o.v = make_uint4(a.x, a.y, o.etc.x, o.etc.y); }
+    }
+    return ERR_OK;
+}
+
+}  // namespace b2bu

@@ -1,0 +1,361 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native Basis Universal transcoder.
+
+Contract (one JSON line on stdout from rank 0):
+  metric   Gtexels/s of the UASTC -> ASTC 4x4 transcode (BASELINE.json configs[1]: synthetic
+           8192x8192 texture = 4,194,304 blocks per step per GPU)
+  value    device-resident throughput (inputs already in HBM, CUDA events on the launching stream,
+           max over ranks), whole job over all N GPUs (weak scaling: every GPU transcodes its own texture)
+  e2e      the same metric through the reference-facing C-ABI call b2bu_uastc_transcode() with
+           pinned HOST buffers: H2D + kernels + D2H inside the timed region
+  roofline achieved algorithmic GB/s (32 B per block) of the K1<ASTC> kernel vs
+           the measured HBM copy peak
+  cpu_baseline  the CPU oracle port (C restatement of the reference's scalar path) on the host cores
+--impl reference times that CPU port on all host threads instead (the reference is Rust and cannot
+be built in this image).
+"""
+import argparse
+import ctypes
+import json
+import os
+import pathlib
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import numpy as np
+
+TARGET_NAMES = {"rgba": 0, "astc": 1, "bc7": 2, "etc1": 3, "etc2": 4}
+OUT_BYTES = {0: 64, 1: 16, 2: 16, 3: 8, 4: 16}
+ALGO_BYTES = {0: 80, 1: 32, 2: 32, 3: 24, 4: 32}          # input + output per block
+
+
+def make_payload(kind: str, nblocks: int, seed: int = 0) -> np.ndarray:
+    """Synthetic UASTC payloads of SURVEY.md section 8d, built from the reference's 608 golden input
+    blocks (tests/golden/uastc_kat.bin): kat-coherent = tiled in file order (runs of 32 same-mode
+    blocks), kat-shuffled = same multiset in a seeded permutation, random = valid-random blocks."""
+    if kind == "random":
+        from uastc_synth import random_blocks
+        return random_blocks(nblocks, seed=seed + 1)
+    blob = (ROOT / "tests" / "golden" / "uastc_kat.bin").read_bytes()
+    recs = np.frombuffer(blob, dtype=np.uint8, offset=8).reshape(-1, 137)
+    inputs = np.ascontiguousarray(recs[:, 1:17])
+    reps = (nblocks + len(inputs) - 1) // len(inputs)
+    tiled = np.tile(inputs, (reps, 1))[:nblocks]
+    if kind == "kat-coherent":
+        return np.ascontiguousarray(tiled)
+    if kind == "kat-shuffled":
+        rng = np.random.default_rng(seed)
+        return np.ascontiguousarray(tiled[rng.permutation(nblocks)])
+    raise ValueError(kind)
+
+
+def load_oracle():
+    import conftest
+    L = ctypes.CDLL(str(conftest.build_oracle()))
+    L.orc_uastc_transcode_slice.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p,
+                                            ctypes.c_int, ctypes.c_void_p]
+    return L
+
+
+def time_oracle(L, target, blocks, bpr, threads, min_seconds=2.0, max_reps=50):
+    """Gtexel/s of the CPU port on `blocks` with `threads` threads."""
+    n = blocks.shape[0]
+    out = np.zeros(n * OUT_BYTES[target], dtype=np.uint8)
+    L.orc_uastc_transcode_slice(target, blocks.ctypes.data, n * 16, bpr, out.ctypes.data, threads, None)   # warm
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        e = L.orc_uastc_transcode_slice(target, blocks.ctypes.data, n * 16, bpr, out.ctypes.data, threads, None)
+        assert e == 0
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds or reps >= max_reps:
+            break
+    return reps * n * 16 / dt / 1e9, dt, reps, out
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._halt = index, [], set(), None, threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._halt.wait(0.02)
+
+    def finish(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=1)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(target_name):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(target_name)
+        except Exception:
+            return None
+    return None
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is Rust and this
+    image has no rustc/cargo, so the arm runs the C oracle port (oracle/basisu_oracle.c) with every
+    host thread on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    target = TARGET_NAMES[args.target]
+    cores = os.cpu_count() or 1
+    n = min(args.blocks, args.cpu_sample_blocks)
+    blocks = make_payload(args.payload, args.blocks)[:n]
+    L = load_oracle()
+    out = np.zeros(n * OUT_BYTES[target], dtype=np.uint8)
+    for _ in range(args.warmup):
+        L.orc_uastc_transcode_slice(target, blocks.ctypes.data, n * 16, args.bpr, out.ctypes.data, cores, None)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        assert L.orc_uastc_transcode_slice(target, blocks.ctypes.data, n * 16, args.bpr, out.ctypes.data, cores, None) == 0
+    dt = time.perf_counter() - t0
+    value = args.steps * n * 16 / dt / 1e9
+    sample = f"{n} of {args.blocks} blocks per step ({args.payload}), {cores} threads, static block partition"
+    line = {
+        "impl": "reference", "metric": "Gtexels/s UASTC->%s" % args.target.upper(), "value": value, "unit": "Gtexel/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "UASTC->%s 8192x8192 (%d blocks/step), CPU port on a bounded sample" % (args.target.upper(), args.blocks),
+                   "payload": args.payload, "sample_blocks": n},
+        "cpu_baseline": {"value": value, "unit": "Gtexel/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Gtexel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference (Rust) cannot be built here: no rustc/cargo; this is the C restatement pinned on the reference's 3,040 KATs",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--target", default="astc", choices=list(TARGET_NAMES))
+    ap.add_argument("--payload", default="kat-shuffled", choices=["kat-shuffled", "kat-coherent", "random"])
+    ap.add_argument("--blocks", type=int, default=2048 * 2048)        # 8192 x 8192 texels
+    ap.add_argument("--bpr", type=int, default=2048)
+    ap.add_argument("--ring", type=int, default=4, help="distinct device buffer sets cycled through (ring * 128 MiB > L2)")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--cpu-sample-blocks", type=int, default=1 << 20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--all-targets", action="store_true", help="also report the other targets / payloads in 'extra'")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import basisu_rs_b200 as b
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: basisu_rs_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    L = b.lib()
+    assert L.b2bu_init(local_rank) == 0, L.b2bu_last_cuda_error().decode()
+
+    target = TARGET_NAMES[args.target]
+    n = args.blocks
+    ob = OUT_BYTES[target]
+    blocks = make_payload(args.payload, n, seed=rank)          # each GPU owns its own texture (sharded by image)
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+
+    # ---- device-resident run: ring of distinct input/output buffers, total footprint > L2 ----
+    d_in = [torch.from_numpy(blocks.reshape(-1)).cuda() for _ in range(args.ring)]
+    d_out = [torch.empty(n * ob, dtype=torch.uint8, device="cuda") for _ in range(args.ring)]
+    status = torch.zeros(1, dtype=torch.int64, device="cuda")
+    assert L.b2bu_status_reset_dev(status.data_ptr(), sh) == 0
+
+    def step(i):
+        k = i % args.ring
+        st = L.b2bu_uastc_transcode_dev(target, d_in[k].data_ptr(), n * 16, args.bpr, d_out[k].data_ptr(), n * ob, status.data_ptr(), sh)
+        assert st == 0, L.b2bu_last_cuda_error().decode()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.b2bu_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    ev1.record(stream)
+    barrier()
+    launches = L.b2bu_launch_count() - launches0
+    clocks = sampler.finish()
+    ms = ev0.elapsed_time(ev1)
+    bad = ctypes.c_uint64(0)
+    assert L.b2bu_status_read_dev(status.data_ptr(), sh, ctypes.byref(bad)) == 0, "payload contained invalid blocks"
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = world * n * 16 / (ms_per_step * 1e-3) / 1e9
+
+    # ---- parity on the exact benchmark buffers (rank 0, bounded oracle sample + golden tiling) ----
+    parity = None
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        orc = load_oracle()
+        cores = os.cpu_count() or 1
+        ns = min(n, args.cpu_sample_blocks)
+        ns -= ns % args.bpr if target == 0 and ns >= args.bpr else 0
+        gt, dt, reps, want = time_oracle(orc, target, blocks[:ns], args.bpr, cores)
+        got = d_out[(args.steps - 1) % args.ring][: ns * ob].cpu().numpy()
+        parity = bool((got == want).all()) if target != 0 else None
+        g1, dt1, reps1, _ = time_oracle(orc, target, blocks[: max(ns // 8, 1)], args.bpr, 1, min_seconds=1.0)
+        cpu = {"value": gt, "unit": "Gtexel/s", "cores": cores, "kind": "port",
+               "sample": f"{ns} of {n} blocks x {reps} reps in {dt:.1f} s, {cores} threads (static block partition); 1 thread: {g1:.4f} Gtexel/s",
+               "single_thread_value": g1}
+
+    # ---- end to end: host pinned buffers through the reference-facing C-ABI call ----
+    h_in = torch.from_numpy(blocks.reshape(-1)).pin_memory()
+    h_out = torch.empty(n * ob, dtype=torch.uint8).pin_memory()
+    fb = ctypes.c_uint64(0)
+
+    def e2e_step():
+        if target == 0:
+            st = L.b2bu_uastc_decode_rgba(h_in.data_ptr(), n * 16, args.bpr, h_out.data_ptr(), n * 16, ctypes.byref(fb))
+        else:
+            st = L.b2bu_uastc_transcode(target, h_in.data_ptr(), n * 16, h_out.data_ptr(), n * ob, ctypes.byref(fb))
+        assert st == 0, (st, L.b2bu_last_cuda_error().decode())
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    l0 = L.b2bu_launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_launches = L.b2bu_launch_count() - l0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * 16 * args.e2e_steps / float(te.item()) / 1e9
+    e2e_parity = None
+    if rank == 0 and parity is not None:
+        e2e_parity = bool((h_out[: want.size].numpy() == want).all())
+
+    extra = {}
+    if args.all_targets and rank == 0:
+        for tn, tt in TARGET_NAMES.items():
+            for pk in ("kat-shuffled", "kat-coherent", "random"):
+                blk = make_payload(pk, n)
+                di = torch.from_numpy(blk.reshape(-1)).cuda()
+                do = [torch.empty(n * OUT_BYTES[tt], dtype=torch.uint8, device="cuda") for _ in range(2)]
+                for i in range(3):
+                    L.b2bu_uastc_transcode_dev(tt, di.data_ptr(), n * 16, args.bpr, do[i % 2].data_ptr(), n * OUT_BYTES[tt], status.data_ptr(), sh)
+                torch.cuda.synchronize()
+                a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for i in range(20):
+                    L.b2bu_uastc_transcode_dev(tt, di.data_ptr(), n * 16, args.bpr, do[i % 2].data_ptr(), n * OUT_BYTES[tt], status.data_ptr(), sh)
+                c.record(stream)
+                torch.cuda.synchronize()
+                us = a.elapsed_time(c) / 20 * 1e3
+                extra[f"{tn}/{pk}"] = {"us_per_launch": us, "gtexel_s": n * 16 / us / 1e3, "algo_gb_s": n * ALGO_BYTES[tt] / us / 1e3}
+                del di, do
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        achieved = n * ALGO_BYTES[target] / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": "Gtexels/s UASTC->%s" % args.target.upper(),
+            "value": value, "unit": "Gtexel/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "UASTC->%s 4x4 transcode, synthetic 8192x8192 texture (%d blocks) per GPU per step"
+                                   % (args.target.upper(), n),
+                       "payload": args.payload + " (reference KAT blocks tiled/permuted, seed = rank)",
+                       "l2_policy": "ring of %d distinct in/out buffer sets (%d MiB) cycled, larger than the 126 MB L2"
+                                    % (args.ring, args.ring * n * (16 + ob) >> 20),
+                       "sharding": "one texture per GPU, no collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(args.target), "peak_source": peak_src,
+                         "algorithmic_bytes_per_block": ALGO_BYTES[target], "kernel": "uastc_transcode_kernel<%s>" % args.target.upper()},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "Gtexel/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * ob,
+                    "steps": args.e2e_steps, "launches": int(e2e_launches), "api": "b2bu_uastc_transcode (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "parity": {"device_vs_oracle_sample": parity, "e2e_vs_oracle_sample": e2e_parity},
+        }
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

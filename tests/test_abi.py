@@ -1,0 +1,62 @@
+"""The C-ABI library must load and export every symbol include/b2bu.h declares (no compute here)."""
+import ctypes
+import pathlib
+import re
+
+import numpy as np
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "b2bu.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2bu_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import basisu_rs_b200 as b
+    path = b.library_path()
+    assert path.exists(), "run `python -m basisu_rs_b200.build` (or __graft_entry__.build()) first"
+    L = ctypes.CDLL(str(path))
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/b2bu.h but not exported"
+
+
+def test_host_only_entry_points_work_without_gpu():
+    import basisu_rs_b200 as b
+    from basis_writer import uastc_file, crc16
+    L = b.lib()
+    assert L.b2bu_block_bytes(0) == 64 and L.b2bu_block_bytes(3) == 8 and L.b2bu_block_bytes(2) == 16
+    assert L.b2bu_error_string(2) == b"invalid mode index"
+    assert L.b2bu_error_string(3) == b"block pattern is not valid"
+    assert L.b2bu_error_string(1) == b"data length is not divisible by UASTC block size (16)"
+    d = bytes(range(200))
+    assert L.b2bu_crc16(d, len(d), 0) == crc16(d)
+    blocks = np.zeros((6, 16), dtype=np.uint8).tobytes()
+    f = uastc_file(blocks, 3, 2)
+    h = b.read_header(f)
+    assert (h.sig, h.header_size, h.total_slices, h.tex_format) == (0x4273, 77, 1, 1)
+    assert h.texture_format() == "UASTC4x4" and not h.has_alpha()
+    # sizing call (out == NULL) does not touch the GPU
+    cnt = ctypes.c_uint32(0)
+    need = ctypes.c_uint64(0)
+    imgs = (b._CImage * 4)()
+    st = L.b2bu_read_to(b.BC7, f, len(f), None, imgs, 4, ctypes.byref(cnt), None, 0, ctypes.byref(need))
+    assert (st, cnt.value, need.value) == (0, 1, 6 * 16)
+    assert (imgs[0].w, imgs[0].h, imgs[0].stride) == (12, 8, 48)
+    for corrupt, code in (("sig", 9), ("header", 11), ("data", 12)):
+        g = uastc_file(blocks, 3, 2, corrupt=corrupt)
+        assert L.b2bu_read_to(b.BC7, g, len(g), None, None, 0, ctypes.byref(cnt), None, 0, ctypes.byref(need)) == code
+    assert L.b2bu_read_to(b.BC7, f, 40, None, None, 0, ctypes.byref(cnt), None, 0, ctypes.byref(need)) == 10
+
+
+def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
+    import basisu_rs_b200 as b
+    monkeypatch.setattr(b, "_LIB", None)
+    monkeypatch.setattr(b, "_HERE", tmp_path)
+    with pytest.raises(ImportError):
+        b.lib()

@@ -1,0 +1,44 @@
+"""CPU tests of the KERNEL SOURCE itself: basisu_rs_b200/csrc/uastc_device.cuh compiled for the host
+with shimmed intrinsics (tests/emu).  Catches logic errors before any GPU time is spent; the real
+parity gate is tests/test_gpu_uastc.py on the B200."""
+import numpy as np
+import pytest
+
+from conftest import OUT_BYTES, TARGETS, oracle_transcode, rgba_image_to_blocks
+from uastc_synth import random_blocks
+
+
+def emu_transcode(emu, target, blocks, bpr=1):
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
+    n = blocks.shape[0]
+    out = np.zeros(n * OUT_BYTES[target], dtype=np.uint8)
+    st = emu.emu_uastc_transcode(target, blocks.ctypes.data, n, bpr, out.ctypes.data)
+    return st, out
+
+
+@pytest.mark.parametrize("name", list(TARGETS))
+def test_kernel_source_reproduces_kat_vectors(emu, kat, name):
+    t = TARGETS[name]
+    st, out = emu_transcode(emu, t, kat.inputs)
+    assert st == 0xFFFFFFFFFFFFFFFF
+    assert (out.reshape(kat.n, OUT_BYTES[t]) == kat.expected[t]).all()
+
+
+@pytest.mark.parametrize("name", list(TARGETS))
+def test_kernel_source_matches_oracle_on_random_valid_blocks(emu, oracle, name):
+    t = TARGETS[name]
+    n, bpr = 60000, 100
+    blk = random_blocks(n, seed=11)
+    st, a = emu_transcode(emu, t, blk, bpr)
+    e, _, b = oracle_transcode(oracle, t, blk, bpr)
+    assert st == 0xFFFFFFFFFFFFFFFF and e == 0
+    assert (a == b).all()
+
+
+def test_kernel_source_error_codes(emu, oracle):
+    blk = random_blocks(5000, seed=5, invalid_fraction=0.01)
+    for t in range(5):
+        st, _ = emu_transcode(emu, t, blk, 100)
+        e, bad, _ = oracle_transcode(oracle, t, blk, 100, threads=1)
+        assert e in (2, 3)
+        assert (st >> 8, st & 0xFF) == (bad, e)
