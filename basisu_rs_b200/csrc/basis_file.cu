@@ -127,7 +127,8 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
             const uint64_t nb = s.file_size / 16;
             if (target == B2BU_RGBA && (s.num_blocks_x == 0 || nb % s.num_blocks_x != 0)) return B2BU_ERR_RANGE;
             im.nbytes = nb * b2bu_block_bytes(target);
-            im.stride = (uint32_t)b2bu_block_bytes(target) * s.num_blocks_x;                     // basis.rs:78-84,131-135
+            // RGBA: 4*nbx Color32 per row, x4 in into_rgba_bytes (basis.rs:78-84, lib.rs:71-78); else block_bytes*nbx (:131-135)
+            im.stride = (target == B2BU_RGBA ? 16u : (uint32_t)b2bu_block_bytes(target)) * s.num_blocks_x;
         }
         total += im.nbytes;
     }

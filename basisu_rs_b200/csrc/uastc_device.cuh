@@ -961,10 +961,10 @@ template <int M> B2BU_DI bool header_ok(const uint4& b, uint32_t& pat, uint32_t&
     return pat < (uint32_t)MD<M>::PCOUNT;          // uastc.rs:360-365
 }
 
+// mode = T.mode_lut[low 7 bits] (uastc.rs:329-341); 19 = invalid code
 template <int TARGET>
-B2BU_DI uint32_t transcode_one(const uint4& b, const DevTables& T, BlockOut& o)
+B2BU_DI uint32_t transcode_mode(uint32_t mode, const uint4& b, const DevTables& T, BlockOut& o)
 {
-    const uint32_t mode = T.mode_lut[b.x & 127u];  // uastc.rs:329-341
     uint32_t pat = 0, compsel = 0;
     if (mode == 8u) {
         const uint32_t c = mode8_rgba(b);
@@ -1004,6 +1004,12 @@ B2BU_DI uint32_t transcode_one(const uint4& b, const DevTables& T, BlockOut& o)
         if (TARGET == TGT_ETC2) { const uint2 a = etc2_alpha_block(o.px, f.etc2tm, T); o.v = make_uint4(a.x, a.y, o.etc.x, o.etc.y); }
     }
     return ERR_OK;
+}
+
+template <int TARGET>
+B2BU_DI uint32_t transcode_one(const uint4& b, const DevTables& T, BlockOut& o)
+{
+    return transcode_mode<TARGET>(T.mode_lut[b.x & 127u], b, T, o);
 }
 
 }  // namespace b2bu
