@@ -363,14 +363,13 @@ __host__ __device__ constexpr uint32_t astc_block_mode(int m)                   
          : m == 13 ? 0x0441 : m == 14 ? 0x0042 : m == 15 ? 0x0242 : m == 16 ? 0x0842 : m == 17 ? 0x0442 : m == 18 ? 0x0253 : 0;
 }
 
-// mask with wbits ones at every texel of `subset` in a 2-bit-per-texel map
-template <int WB> B2BU_DI uint64_t subset_field_mask(uint32_t pw, uint32_t subset)
+// Mask with WB ones at every texel of `subset`, from the 2-bit-per-texel subset map.  WB == 2 is
+// pure arithmetic on the map; WB == 3 (UASTC mode 2 only) uses the pre-expanded 2-subset table.
+B2BU_DI uint32_t subset_mask2(uint32_t pw, uint32_t subset)
 {
-    uint64_t m = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++)
-        if (((pw >> (2 * i)) & 3u) == subset) m |= (uint64_t)((1u << WB) - 1u) << (WB * i);
-    return m;
+    const uint32_t lo = pw & 0x55555555u, hi = (pw >> 1) & 0x55555555u;      // subset bit 0 / bit 1 per texel
+    const uint32_t sel = subset == 0u ? (~(lo | hi) & 0x55555555u) : subset == 1u ? lo : hi;
+    return sel * 3u;
 }
 
 template <int M> B2BU_DI uint4 astc_block(const uint4& b, const DevTables& T, uint32_t pat, uint32_t compsel)
@@ -463,12 +462,21 @@ template <int M> B2BU_DI uint4 astc_block(const uint4& b, const DevTables& T, ui
     if (D::subsets == 1) {
         if (inv[0]) U = xor128(U, mask128(D::WUNI));
     } else {
-        const uint32_t pw = pattern_word<M>(T, pat);
-        uint64_t x = 0;
+        if (D::wbits == 3) {
+            // mode 2: two subsets, 3-bit weights; pat2w3 = texels of subset 1 expanded to 3 bits each
+            const uint64_t m1 = T.pat2w3[pat];
+            uint64_t x = 0;
+            if (inv[0]) x |= ~m1 & 0xFFFFFFFFFFFFull;
+            if (inv[1]) x |= m1;
+            U = xor128(U, u64_to_128(x));
+        } else {
+            const uint32_t pw = pattern_word<M>(T, pat);
+            uint32_t x = 0;
 #pragma unroll
-        for (int s = 0; s < D::subsets; s++)
-            if (inv[s]) x |= subset_field_mask<D::wbits>(pw, s);
-        U = xor128(U, u64_to_128(x));
+            for (int s = 0; s < D::subsets; s++)
+                if (inv[s]) x |= subset_mask2(pw, (uint32_t)s);
+            U.x ^= x;
+        }
     }
     const uint4 Wrev = make_uint4(__brev(U.w), __brev(U.z), __brev(U.y), __brev(U.x));
     out = or128(out, Wrev);

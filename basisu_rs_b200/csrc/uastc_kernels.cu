@@ -28,6 +28,15 @@ __device__ __forceinline__ void load_tables(DevTables* dst)
     __syncthreads();
 }
 
+// shared-memory atomic add with the address space made explicit (the generic form costs ~10 instructions)
+__device__ __forceinline__ uint32_t atom_add_shared(uint32_t* p, uint32_t v)
+{
+    uint32_t old;
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
+}
+
 __device__ __forceinline__ void report_error(unsigned long long* err, uint64_t block_index, uint32_t code)
 {
     // first failing block wins (uastc.rs:161-163: the first Err aborts the slice)
@@ -85,16 +94,23 @@ template <int TARGET> struct SortedCfg {
     static constexpr int OB = TARGET == TGT_RGBA ? 64 : TARGET == TGT_ETC1 ? 8 : 16;
     static constexpr int MAXORD = TILE + kBins * 32;
     static constexpr int MAXITEMS = MAXORD / 32;
+    // ASTC / BC7 / ETC1 / ETC2 results overwrite the block's own 16-byte input slot (read once by the
+    // same thread just before); only RGBA (64 B per block) needs a separate staging buffer
+    static constexpr bool IN_PLACE = OB <= 16;
+    static constexpr int CTAS_PER_SM = TARGET == TGT_ASTC ? 3 : 2;
+    // work-item scheduling inside a tile: ASTC items are short and even, a static round-robin beats the
+    // shared counter; the heavier, more uneven targets (BC7, RGBA, ETC) gain from dynamic pulls
+    static constexpr bool DYNAMIC = TARGET != TGT_ASTC;
     static constexpr size_t OFF_IN = sizeof(DevTables);
-    static constexpr size_t OFF_OUT = OFF_IN + (size_t)TILE * 16;
-    static constexpr size_t OFF_ORDER = OFF_OUT + (size_t)TILE * OB;
+    static constexpr size_t OFF_OUT = IN_PLACE ? OFF_IN : OFF_IN + (size_t)TILE * 16;
+    static constexpr size_t OFF_ORDER = OFF_OUT + (size_t)TILE * (IN_PLACE ? 16 : OB);
     static constexpr size_t OFF_IMODE = OFF_ORDER + (size_t)MAXORD * 2;
     static constexpr size_t OFF_CNT = (OFF_IMODE + MAXITEMS + 15) / 16 * 16;
     static constexpr size_t SMEM = OFF_CNT + 4 * (32 + 32 + 4);
 };
 
 template <int TARGET>
-__global__ void __launch_bounds__(SortedCfg<TARGET>::THREADS, 2)
+__global__ void __launch_bounds__(SortedCfg<TARGET>::THREADS, SortedCfg<TARGET>::CTAS_PER_SM)
 uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64_t nblocks, uint32_t blocks_per_row,
                     uint64_t index_base, unsigned long long* __restrict__ err)
 {
@@ -121,21 +137,26 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
         // ---- A: load the tile, classify, rank inside each mode bin ----
         for (int i = tid; i < C::MAXORD; i += C::THREADS) order[i] = 0xFFFFu;
         uint32_t mymode[C::PER], mypos[C::PER];
+        uint4 blk[C::PER];
+#pragma unroll
+        for (int k = 0; k < C::PER; k++) {                 // all global loads in flight before any use
+            const uint32_t idx = tid + k * C::THREADS;
+            blk[k] = idx < nt ? __ldg(in + base + idx) : make_uint4(0u, 0u, 0u, 0u);
+        }
 #pragma unroll
         for (int k = 0; k < C::PER; k++) {
             const uint32_t idx = tid + k * C::THREADS;
-            uint32_t m = 31u;
-            if (idx < nt) {
-                const uint4 b = __ldg(in + base + idx);
-                in_s[idx] = b;
-                m = T.mode_lut[b.x & 127u];
-            }
+            in_s[idx] = blk[k];
+            mymode[k] = idx < nt ? (uint32_t)T.mode_lut[blk[k].x & 127u] : 31u;
+        }
+#pragma unroll
+        for (int k = 0; k < C::PER; k++) {
+            const uint32_t m = mymode[k];
             const uint32_t peers = __match_any_sync(0xFFFFFFFFu, m);
             const int leader = __ffs(peers) - 1;
             uint32_t p0 = 0;
-            if (lane == leader && m < (uint32_t)kBins) p0 = atomicAdd(&cnt[m], __popc(peers));
+            if (lane == leader && m < (uint32_t)kBins) p0 = atom_add_shared(&cnt[m], __popc(peers));
             p0 = __shfl_sync(0xFFFFFFFFu, p0, leader);
-            mymode[k] = m;
             mypos[k] = p0 + __popc(peers & ((1u << lane) - 1u));
         }
         __syncthreads();
@@ -160,10 +181,12 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
         __syncthreads();
         // ---- D: warps pull mode-uniform work items ----
         const uint32_t nitems = ctl[1];
-        for (;;) {
-            uint32_t item = 0;
-            if (lane == 0) item = atomicAdd(&ctl[0], 1u);
-            item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        for (uint32_t it = tid >> 5;; it += C::THREADS / 32) {
+            uint32_t item = it;
+            if (C::DYNAMIC) {
+                if (lane == 0) item = atom_add_shared(&ctl[0], 1u);
+                item = __shfl_sync(0xFFFFFFFFu, item, 0);
+            }
             if (item >= nitems) break;
             const uint32_t mode = item_mode[item];
             const uint32_t idx = order[item * 32 + lane];
@@ -182,7 +205,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
                     for (int y = 0; y < 4; y++)
                         reinterpret_cast<uint4*>(out_s)[y * C::TILE + idx] = make_uint4(o.px[4 * y], o.px[4 * y + 1], o.px[4 * y + 2], o.px[4 * y + 3]);
                 } else if (TARGET == TGT_ETC1) {
-                    reinterpret_cast<uint2*>(out_s)[idx] = o.etc;
+                    reinterpret_cast<uint2*>(out_s)[idx * 2] = o.etc;          // first half of the block's own slot
                 } else {
                     reinterpret_cast<uint4*>(out_s)[idx] = o.v;
                 }
@@ -205,13 +228,13 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
             }
         } else if (TARGET == TGT_ETC1) {
             uint2* dst = reinterpret_cast<uint2*>(out) + base;
-            for (uint32_t i = tid; i < nt; i += C::THREADS) dst[i] = reinterpret_cast<const uint2*>(out_s)[i];
+            for (uint32_t i = tid; i < nt; i += C::THREADS) dst[i] = reinterpret_cast<const uint2*>(out_s)[i * 2];
         } else {
             uint4* dst = reinterpret_cast<uint4*>(out) + base;
             for (uint32_t i = tid; i < nt; i += C::THREADS) dst[i] = reinterpret_cast<const uint4*>(out_s)[i];
         }
-        // no barrier needed here: the next tile's phase A only touches order / in_s / cnt, which were last
-        // read before the barrier that precedes phase E; out_s is next written after three more barriers
+        // the next tile's phase A overwrites in_s (== out_s for the in-place targets) and order
+        if (C::IN_PLACE) __syncthreads();
     }
 }
 
@@ -229,7 +252,7 @@ static cudaError_t launch_sorted(const uint4* in, void* d_out, uint64_t nblocks,
         configured[dev] = true;
     }
     const uint64_t ntiles = (nblocks + C::TILE - 1) / C::TILE;
-    const uint64_t cap = (uint64_t)sm_count * 2;
+    const uint64_t cap = (uint64_t)sm_count * C::CTAS_PER_SM;
     const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
     uastc_sorted_kernel<TARGET><<<grid, C::THREADS, C::SMEM, stream>>>(in, d_out, nblocks, bpr, index_base, d_err);
     return cudaGetLastError();

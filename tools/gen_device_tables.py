@@ -100,6 +100,7 @@ def main():
     out.append(carr("pat2", pack_pat(p2) + [0, 0]))
     out.append(carr("pat3", pack_pat(p3) + [0]))
     out.append(carr("pat23", pack_pat(p23) + [0]))
+    out.append(carr("pat2w3", ["0x%Xull" % sum(7 << (3 * i) for i, v in enumerate(r) if v == 1) for r in p2] + ["0", "0"]))
     def anc(rows, pats):
         res = []
         for a, pat in zip(rows, pats):
