@@ -43,7 +43,9 @@ class BasisuError(Exception):
 
 
 def library_path() -> pathlib.Path:
-    return _HERE / "libb2bu.so"
+    import os
+    override = os.environ.get("B2BU_LIBRARY")          # tuning variants built by basisu_rs_b200.build --out=...
+    return pathlib.Path(override) if override else _HERE / "libb2bu.so"
 
 
 def lib() -> ctypes.CDLL:

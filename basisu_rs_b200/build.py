@@ -34,20 +34,22 @@ def needs_build():
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: tuning variants (e.g. defines=["-DB2BU_TILE=2048"], out="libb2bu_t2048.so")."""
+    lib = HERE / out if out else LIB
+    if not force and not out and not needs_build():
         return LIB
     objs = []
     procs = []
-    builddir = HERE / "build"
-    builddir.mkdir(exist_ok=True)
+    builddir = HERE / "build" / (out or "default")
+    builddir.mkdir(parents=True, exist_ok=True)
     nvcc = _nvcc()
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     for src in SOURCES:
         if not (CSRC / src).exists():
             continue
         obj = builddir / (src + ".o")
-        cmd = [nvcc] + flags + ["-Xptxas", "-v"] * int(verbose) + ["-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc] + flags + list(defines) + ["-Xptxas", "-v"] * int(verbose) + ["-c", str(CSRC / src), "-o", str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(str(obj))
     for src, p in procs:
@@ -56,14 +58,16 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
-    link = [nvcc, "-shared", "-o", str(LIB)] + objs + ["-Xcompiler", "-fPIC", "-lcudart_static", "-lpthread", "-ldl", "-lrt",
+    link = [nvcc, "-shared", "-o", str(lib)] + objs + ["-Xcompiler", "-fPIC", "-lcudart_static", "-lpthread", "-ldl", "-lrt",
                                                        "-Xlinker", "--exclude-libs,ALL"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))
