@@ -1,12 +1,430 @@
-// TEMPORARY: ETC1S entry points are wired up after the UASTC path is parity-green on the GPU.
+// ETC1S / BasisLZ host side of the C ABI.
+//
+// Once per file (basis_lz::Decoder::new, reference src/basis_lz/mod.rs:64-95): decode the endpoint
+// and selector codebooks and the four slice Huffman models on the host, exactly as the reference
+// does (they are small and serial), then upload them: codebooks as flat u32 arrays, each Huffman
+// model as a 10-bit first-level table for shared memory plus the reference's full flat table.
+// Per call: upload the slice bitstreams, run K2 (one warp per slice) and K3 (gather), copy back.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../../include/b2bu.h"
+#include "etc1s_device.h"
 #include "etc1s_host.h"
+#include "host_internal.h"
+
 namespace b2bu {
-int etc1s_read_file(int, const uint8_t*, size_t, const b2bu_header&, const SliceDesc*, const b2bu_image*, uint32_t, bool, uint8_t*) { return B2BU_ERR_UNIMPLEMENTED; }
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+// ---- bit cursor: LSB first, bytes past the end read as zero (src/bitreader.rs:27-60) ----------
+struct BitCursor {
+    const uint8_t* p; size_t len; uint64_t pos = 0;
+    BitCursor(const uint8_t* d, size_t n) : p(d), len(n) {}
+    uint32_t peek(unsigned n) const
+    {
+        uint64_t v = 0;
+        const size_t byte = (size_t)(pos >> 3);
+        for (int i = 0; i < 8; i++) if (byte + i < len) v |= (uint64_t)p[byte + i] << (8 * i);
+        v >>= (pos & 7);
+        return n >= 32 ? (uint32_t)v : (uint32_t)(v & ((1ull << n) - 1));
+    }
+    uint32_t read(unsigned n) { const uint32_t v = peek(n); pos += n; return v; }
+};
+
+// ---- Huffman model (src/basis_lz/huffman.rs) ---------------------------------------------------
+struct HuffModel {
+    std::vector<uint32_t> flat;     // 1 << max_len entries of symbol << 5 | code size (0 = no code), as huffman.rs:151-170 fills them
+    unsigned max_len = 0;
+};
+
+static uint32_t bit_reverse32(uint32_t x)
+{
+    x = (x >> 16) | (x << 16);
+    x = ((x & 0xFF00FF00u) >> 8) | ((x & 0x00FF00FFu) << 8);
+    x = ((x & 0xF0F0F0F0u) >> 4) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x & 0xCCCCCCCCu) >> 2) | ((x & 0x33333333u) << 2);
+    return ((x & 0xAAAAAAAAu) >> 1) | ((x & 0x55555555u) << 1);
 }
+
+// huffman.rs:133-184 from_sizes: canonical codes in ascending symbol order, bit-reversed, every
+// table slot whose low `size` bits equal the code is filled (later symbols overwrite earlier ones)
+static int huff_from_sizes(const std::vector<uint8_t>& sizes, HuffModel& m)
+{
+    uint32_t count[17] = {0}, next[17] = {0};
+    unsigned max_len = 0;
+    for (uint8_t s : sizes) {
+        if (s > 16) return B2BU_ERR_HUFFMAN;
+        count[s]++;
+        if (s > max_len) max_len = s;
+    }
+    count[0] = 0;
+    uint32_t total = 0;
+    for (unsigned b = 1; b <= 16; b++) { total = (total + count[b - 1]) << 1; next[b] = total; }
+    m.max_len = max_len;
+    m.flat.assign((size_t)1 << max_len, 0u);
+    for (size_t sym = 0; sym < sizes.size(); sym++) {
+        const unsigned size = sizes[sym];
+        if (!size) continue;
+        const uint32_t code = (bit_reverse32(next[size]) >> (32 - size)) & 0xFFFFu;
+        const uint32_t variants = (1u << (max_len - size)) & 0xFFFFu;              // u16 in the reference
+        for (uint32_t fill = 0; fill < variants; fill++) {
+            const size_t id = (size_t)((((fill << size) & 0xFFFFu) | code));
+            if (id >= m.flat.size()) return B2BU_ERR_HUFFMAN;                       // the reference would panic (index out of bounds)
+            m.flat[id] = ((uint32_t)sym << 5) | size;
+        }
+        next[size]++;
+    }
+    for (unsigned b = 0; b <= 16; b++) if (next[b] > 65536u) return B2BU_ERR_HUFFMAN;   // "codes don't fit into 16 bits"
+    return B2BU_OK;
+}
+
+static int huff_decode_host(const HuffModel& m, BitCursor& c, uint32_t& sym)       // huffman.rs:186-198
+{
+    const uint32_t e = m.flat[c.peek(m.max_len)];
+    if ((e & 31u) == 0) return B2BU_ERR_HUFFMAN;
+    c.pos += e & 31u;
+    sym = e >> 5;
+    return B2BU_OK;
+}
+
+// huffman.rs:43-118 read_huffman_table
+static int read_huffman_table(BitCursor& c, HuffModel& out)
+{
+    static const uint8_t order[21] = {17, 18, 19, 20, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15, 16};
+    const size_t total_used_syms = c.read(14);
+    const unsigned num_cl = c.read(5);
+    if (num_cl > 21) return B2BU_ERR_HUFFMAN;                                      // the reference would panic
+    std::vector<uint8_t> cl_sizes(21, 0);
+    for (unsigned i = 0; i < num_cl; i++) cl_sizes[order[i]] = (uint8_t)c.read(3);
+    HuffModel cl;
+    int st = huff_from_sizes(cl_sizes, cl);
+    if (st) return st;
+    std::vector<uint8_t> sizes;
+    sizes.reserve(total_used_syms + 140);
+    while (sizes.size() < total_used_syms) {
+        uint32_t s;
+        if ((st = huff_decode_host(cl, c, s))) return st;
+        if (s <= 16) sizes.push_back((uint8_t)s);
+        else if (s == 17) sizes.insert(sizes.end(), 3 + c.read(3), 0);
+        else if (s == 18) sizes.insert(sizes.end(), 11 + c.read(7), 0);
+        else {
+            if (sizes.empty() || sizes.back() == 0) return B2BU_ERR_HUFFMAN;       // huffman.rs:82-91, :98-107
+            const uint8_t prev = sizes.back();
+            const size_t n = s == 19 ? 3 + c.read(2) : 7 + c.read(7);
+            sizes.insert(sizes.end(), n, prev);
+        }
+    }
+    return huff_from_sizes(sizes, out);
+}
+
+// first-level table for shared memory: an entry is usable iff every flat slot that shares its low
+// 10 bits holds the same short code; otherwise the kernel falls back to the flat table
+static void build_l1(const HuffModel& m, uint32_t* l1)
+{
+    const unsigned L = 10;
+    for (uint32_t i = 0; i < (1u << L); i++) {
+        if (m.max_len <= L) { l1[i] = m.flat[i & ((1u << m.max_len) - 1u)]; continue; }
+        const uint32_t first = m.flat[i];
+        bool same = true;
+        for (uint32_t k = 1; k < (1u << (m.max_len - L)) && same; k++) same = m.flat[i | (k << L)] == first;
+        l1[i] = (same && (first & 31u) <= L) ? first : 0xFFFFFFFFu;
+    }
+}
+
+}  // namespace b2bu
+
+using namespace b2bu;
+
+struct b2bu_etc1s {
+    int device = 0;
+    uint32_t num_endpoints = 0, num_selectors = 0, hist_size = 0;
+    bool is_video = false;
+    uint32_t max_len[4] = {0, 0, 0, 0};
+    // device copies
+    uint32_t* d_endpoints = nullptr;     // inten | r5 << 8 | g5 << 16 | b5 << 24
+    uint32_t* d_sel_plain = nullptr;     // 4 rows, 2 bits per x          (etc.rs:343-361)
+    uint32_t* d_sel_etc1 = nullptr;      // ETC1 bit planes               (etc.rs:363-393)
+    uint32_t* d_l1 = nullptr;            // 4 x 1024
+    uint32_t* d_flat[4] = {nullptr, nullptr, nullptr, nullptr};
+    // per-call scratch (grow only)
+    void* d_data = nullptr; size_t data_cap = 0;
+    void* d_idx = nullptr; size_t idx_cap = 0;
+    void* d_out = nullptr; size_t out_cap = 0;
+    void* d_scratch = nullptr; size_t scratch_cap = 0;
+    void* d_jobs = nullptr; size_t jobs_cap = 0;
+    void* d_status = nullptr; size_t status_cap = 0;
+    std::mutex mu;
+};
+
+namespace b2bu {
+
+// etc.rs:363-393 Selector::set_selector for a whole selector (4 row bytes) -> ETC1 bit planes
+static uint32_t selector_etc1_bytes(const uint8_t rows[4])
+{
+    static const uint8_t to_etc1[4] = {3, 2, 0, 1};
+    uint8_t b[4] = {0, 0, 0, 0};
+    for (unsigned y = 0; y < 4; y++)
+        for (unsigned x = 0; x < 4; x++) {
+            const unsigned mod = to_etc1[(rows[y] >> (2 * x)) & 3];
+            const unsigned pixel = x * 4 + y, ms = 1 - pixel / 8, ls = ms + 2, bit = pixel % 8;
+            b[ls] |= (uint8_t)((mod & 1) << bit);
+            b[ms] |= (uint8_t)((mod >> 1) << bit);
+        }
+    return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+}
+
+static int upload(uint32_t** dst, const std::vector<uint32_t>& v)
+{
+    CK(cudaMalloc(dst, std::max<size_t>(v.size(), 1) * sizeof(uint32_t)));
+    if (!v.empty()) CK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return B2BU_OK;
+}
+
+struct SliceReq { const uint8_t* data; uint64_t len; uint32_t nbx, nby; };
+struct ImageReq { int rgb_slice, alpha_slice; uint64_t out_ofs; };      // indices into the slice list; alpha_slice = -1 if none
+
+// Decodes `slices` with K2 and emits one output per image with K3.  target: B2BU_ETC1 (images = slices)
+// or B2BU_RGBA (an image may combine an rgb and an alpha slice).
+static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& slices, const std::vector<ImageReq>& images, uint8_t* out,
+                     uint64_t out_total)
+{
+    DeviceCtx* c;
+    int st = get_ctx(&c);
+    if (st) return st;
+    std::lock_guard<std::mutex> lk(h->mu);
+    const size_t ns = slices.size();
+    if (ns == 0) return B2BU_OK;
+    std::vector<Etc1sSliceJob> jobs(ns);
+    uint64_t data_total = 0, blocks_total = 0, scratch_total = 0;
+    for (size_t i = 0; i < ns; i++) {
+        jobs[i].data_ofs = data_total; jobs[i].data_len = slices[i].len;
+        jobs[i].out_ofs = blocks_total; jobs[i].scratch_ofs = scratch_total;
+        jobs[i].nbx = slices[i].nbx; jobs[i].nby = slices[i].nby;
+        data_total += (slices[i].len + 15) & ~15ull;
+        blocks_total += (uint64_t)slices[i].nbx * slices[i].nby;
+        scratch_total += ((slices[i].nbx + 15ull) & ~15ull) + (h->hist_size > 64 ? ((2ull * h->hist_size + 15) & ~15ull) : 0);
+    }
+    if ((st = ensure(&h->d_data, &h->data_cap, data_total + 16))) return st;
+    if ((st = ensure(&h->d_idx, &h->idx_cap, blocks_total * 4 + 16))) return st;
+    if ((st = ensure(&h->d_out, &h->out_cap, out_total + 16))) return st;
+    if ((st = ensure(&h->d_scratch, &h->scratch_cap, scratch_total + 16))) return st;
+    if ((st = ensure(&h->d_jobs, &h->jobs_cap, ns * sizeof(Etc1sSliceJob)))) return st;
+    if ((st = ensure(&h->d_status, &h->status_cap, ns * 4))) return st;
+    cudaStream_t s = c->streams[0];
+    for (size_t i = 0; i < ns; i++)
+        if (slices[i].len) CK(cudaMemcpyAsync(static_cast<uint8_t*>(h->d_data) + jobs[i].data_ofs, slices[i].data, slices[i].len, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_jobs, jobs.data(), ns * sizeof(Etc1sSliceJob), cudaMemcpyHostToDevice, s));
+
+    Etc1sDecodeParams P;
+    P.data = static_cast<const uint8_t*>(h->d_data);
+    P.jobs = static_cast<const Etc1sSliceJob*>(h->d_jobs);
+    P.num_slices = (uint32_t)ns;
+    P.out_idx = static_cast<uint32_t*>(h->d_idx);
+    P.scratch = static_cast<uint8_t*>(h->d_scratch);
+    P.l1 = h->d_l1;
+    for (int t = 0; t < 4; t++) { P.flat[t] = h->d_flat[t]; P.max_len[t] = h->max_len[t]; }
+    P.num_endpoints = h->num_endpoints; P.num_selectors = h->num_selectors; P.hist_size = h->hist_size; P.is_video = h->is_video ? 1u : 0u;
+    P.status = static_cast<uint32_t*>(h->d_status);
+    // one warp per slice; spread slices over SMs first, pack warps only when there are many slices
+    const int warps = ns >= (size_t)c->sm_count * 8 ? 4 : 1;
+    CK(launch_etc1s_decode(P, warps, s));
+    count_launch(1);
+
+    const uint32_t* idx = static_cast<const uint32_t*>(h->d_idx);
+    if (target == B2BU_ETC1) {
+        // images are the slices in order and ETC1 output does not depend on the slice shape: one gather over everything
+        CK(launch_etc1s_gather_etc1(idx, blocks_total, h->d_endpoints, h->d_sel_etc1, h->d_out, c->sm_count, s));
+        count_launch(1);
+    } else {
+        for (const ImageReq& im : images) {
+            const Etc1sSliceJob& j = jobs[im.rgb_slice];
+            const uint32_t* ia = im.alpha_slice >= 0 ? idx + jobs[im.alpha_slice].out_ofs : nullptr;
+            CK(launch_etc1s_gather_rgba(idx + j.out_ofs, ia, j.nbx, (uint64_t)j.nbx * j.nby, h->d_endpoints, h->d_sel_plain,
+                                        static_cast<uint8_t*>(h->d_out) + im.out_ofs, c->sm_count, s));
+            count_launch(1);
+        }
+    }
+    std::vector<uint32_t> status(ns);
+    CK(cudaMemcpyAsync(status.data(), h->d_status, ns * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out, h->d_out, out_total, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < ns; i++) if (status[i]) return (int)status[i];          // first failing slice in file order
+    return B2BU_OK;
+}
+
+static int etc1s_open_impl(uint32_t endpoint_count, uint32_t selector_count, const uint8_t* ep, size_t ep_len, const uint8_t* sel, size_t sel_len,
+                           const uint8_t* tab, size_t tab_len, bool is_video, b2bu_etc1s** out)
+{
+    DeviceCtx* c;
+    int st = get_ctx(&c);
+    if (st) return st;
+    std::unique_ptr<b2bu_etc1s> h(new b2bu_etc1s);
+    h->device = c->device;
+    h->num_endpoints = endpoint_count; h->num_selectors = selector_count; h->is_video = is_video;
+
+    // ---- endpoint codebook (mod.rs:461-516) ----
+    std::vector<uint32_t> endpoints(endpoint_count);
+    {
+        BitCursor bc(ep, ep_len);
+        HuffModel m0, m1, m2, mi;
+        if ((st = read_huffman_table(bc, m0)) || (st = read_huffman_table(bc, m1)) || (st = read_huffman_table(bc, m2)) ||
+            (st = read_huffman_table(bc, mi))) return st;
+        const bool grayscale = bc.read(1) == 1;
+        uint32_t prev[3] = {16, 16, 16}, prev_inten = 0;
+        for (uint32_t i = 0; i < endpoint_count; i++) {
+            uint32_t d;
+            if ((st = huff_decode_host(mi, bc, d))) return st;
+            const uint32_t inten = (d + prev_inten) & 7u;
+            prev_inten = inten;
+            uint32_t col[3];
+            for (int ch = 0; ch < (grayscale ? 1 : 3); ch++) {
+                const HuffModel& m = prev[ch] <= 9 ? m0 : prev[ch] <= 21 ? m1 : m2;
+                if ((st = huff_decode_host(m, bc, d))) return st;
+                col[ch] = (prev[ch] + (d & 0xFFu)) & 31u;                        // u8 wrapping_add, then & 31
+                prev[ch] = col[ch];
+            }
+            if (grayscale) col[1] = col[2] = col[0];
+            endpoints[i] = inten | (col[0] << 8) | (col[1] << 16) | (col[2] << 24);
+        }
+    }
+    // ---- selector codebook (mod.rs:524-583) ----
+    std::vector<uint32_t> sel_plain(selector_count), sel_etc1(selector_count);
+    {
+        BitCursor bc(sel, sel_len);
+        const bool global = bc.read(1) == 1, hybrid = bc.read(1) == 1, raw = bc.read(1) == 1;
+        if (global || hybrid) return B2BU_ERR_SELECTOR_CB;
+        HuffModel m;
+        if (!raw && (st = read_huffman_table(bc, m))) return st;
+        uint8_t prev[4] = {0, 0, 0, 0};
+        for (uint32_t i = 0; i < selector_count; i++) {
+            uint8_t rows[4];
+            for (int y = 0; y < 4; y++) {
+                if (raw || i == 0) rows[y] = (uint8_t)bc.read(8);
+                else {
+                    uint32_t d;
+                    if ((st = huff_decode_host(m, bc, d))) return st;
+                    rows[y] = (uint8_t)((uint8_t)d ^ prev[y]);
+                }
+                prev[y] = rows[y];
+            }
+            sel_plain[i] = (uint32_t)rows[0] | ((uint32_t)rows[1] << 8) | ((uint32_t)rows[2] << 16) | ((uint32_t)rows[3] << 24);
+            sel_etc1[i] = selector_etc1_bytes(rows);
+        }
+    }
+    // ---- slice models (mod.rs:77-83) ----
+    HuffModel models[4];
+    {
+        BitCursor bc(tab, tab_len);
+        for (int t = 0; t < 4; t++) if ((st = read_huffman_table(bc, models[t]))) return st;
+        h->hist_size = bc.read(13);
+    }
+    std::vector<uint32_t> l1(4 * 1024);
+    for (int t = 0; t < 4; t++) { build_l1(models[t], l1.data() + t * 1024); h->max_len[t] = models[t].max_len; }
+
+    CK(cudaSetDevice(h->device));
+    if ((st = upload(&h->d_endpoints, endpoints)) || (st = upload(&h->d_sel_plain, sel_plain)) || (st = upload(&h->d_sel_etc1, sel_etc1)) ||
+        (st = upload(&h->d_l1, l1))) return st;
+    for (int t = 0; t < 4; t++) if ((st = upload(&h->d_flat[t], models[t].flat))) return st;
+    *out = h.release();
+    return B2BU_OK;
+}
+
+int etc1s_read_file(int target, const uint8_t* buf, size_t len, const b2bu_header& hd, const SliceDesc* descs, const b2bu_image* plan,
+                    uint32_t nimg, bool pair, uint8_t* out)
+{
+    // basis.rs:262-300 make_basis_lz_decoder: sections are slices of the file (out of range => the reference panics)
+    if ((uint64_t)hd.endpoint_cb_file_ofs + hd.endpoint_cb_file_size > len || (uint64_t)hd.selector_cb_file_ofs + hd.selector_cb_file_size > len ||
+        (uint64_t)hd.tables_file_ofs + hd.tables_file_size > len || (uint64_t)hd.extended_file_ofs + hd.extended_file_size > len) return B2BU_ERR_RANGE;
+    b2bu_etc1s* h = nullptr;
+    // quirk C-1 (basis.rs:289-291): total_selectors is passed as BOTH the endpoint and the selector count
+    int st = etc1s_open_impl(hd.total_selectors, hd.total_selectors, buf + hd.endpoint_cb_file_ofs, hd.endpoint_cb_file_size,
+                             buf + hd.selector_cb_file_ofs, hd.selector_cb_file_size, buf + hd.tables_file_ofs, hd.tables_file_size,
+                             hd.tex_type == 3, &h);
+    if (st) return st;
+    std::vector<SliceReq> slices;
+    std::vector<ImageReq> images;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < nimg; i++) {
+        const SliceDesc& s = descs[pair ? 2 * i : i];
+        ImageReq im;
+        im.rgb_slice = (int)slices.size();
+        slices.push_back({buf + s.file_ofs, s.file_size, s.num_blocks_x, s.num_blocks_y});
+        im.alpha_slice = -1;
+        if (pair) {
+            const SliceDesc& a = descs[2 * i + 1];
+            im.alpha_slice = (int)slices.size();
+            slices.push_back({buf + a.file_ofs, a.file_size, a.num_blocks_x, a.num_blocks_y});
+        }
+        im.out_ofs = plan[i].offset;
+        images.push_back(im);
+        total = plan[i].offset + plan[i].nbytes;
+    }
+    st = etc1s_run(h, target, slices, images, out, total);
+    b2bu_etc1s_close(h);
+    return st;
+}
+
+}  // namespace b2bu
+
 extern "C" {
-int b2bu_etc1s_open(uint32_t, uint32_t, const uint8_t*, size_t, const uint8_t*, size_t, const uint8_t*, size_t, int, b2bu_etc1s**) { return B2BU_ERR_UNIMPLEMENTED; }
-void b2bu_etc1s_close(b2bu_etc1s*) {}
-int b2bu_etc1s_transcode_to_etc1(b2bu_etc1s*, uint32_t, uint32_t, const uint8_t*, size_t, uint8_t*, size_t) { return B2BU_ERR_UNIMPLEMENTED; }
-int b2bu_etc1s_decode_to_rgba(b2bu_etc1s*, uint32_t, uint32_t, const uint8_t*, size_t, const uint8_t*, size_t, uint8_t*, size_t) { return B2BU_ERR_UNIMPLEMENTED; }
-int b2bu_etc1s_transcode_slices(b2bu_etc1s*, int, uint32_t, uint32_t, const uint8_t*, size_t, const uint64_t*, const uint64_t*, uint32_t, uint8_t*, size_t) { return B2BU_ERR_UNIMPLEMENTED; }
+
+int b2bu_etc1s_open(uint32_t endpoint_count, uint32_t selector_count, const uint8_t* endpoint_data, size_t endpoint_len,
+                    const uint8_t* selector_data, size_t selector_len, const uint8_t* tables_data, size_t tables_len, int is_video,
+                    b2bu_etc1s** handle)
+{
+    if (!handle || !endpoint_data || !selector_data || !tables_data || endpoint_count > 65535 || selector_count > 65535) return B2BU_ERR_ARGUMENT;
+    *handle = nullptr;
+    return etc1s_open_impl(endpoint_count, selector_count, endpoint_data, endpoint_len, selector_data, selector_len, tables_data, tables_len,
+                           is_video != 0, handle);
 }
+
+void b2bu_etc1s_close(b2bu_etc1s* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_endpoints); cudaFree(h->d_sel_plain); cudaFree(h->d_sel_etc1); cudaFree(h->d_l1);
+    for (int t = 0; t < 4; t++) cudaFree(h->d_flat[t]);
+    cudaFree(h->d_data); cudaFree(h->d_idx); cudaFree(h->d_out); cudaFree(h->d_scratch); cudaFree(h->d_jobs); cudaFree(h->d_status);
+    delete h;
+}
+
+int b2bu_etc1s_transcode_slices(b2bu_etc1s* h, int target, uint32_t nbx, uint32_t nby, const uint8_t* data, size_t data_len,
+                                const uint64_t* slice_ofs, const uint64_t* slice_len, uint32_t num_slices, uint8_t* out, size_t out_bytes)
+{
+    if (!h || (target != B2BU_ETC1 && target != B2BU_RGBA) || (num_slices && (!data || !slice_ofs || !slice_len || !out))) return B2BU_ERR_ARGUMENT;
+    const uint64_t per = (uint64_t)nbx * nby * (target == B2BU_ETC1 ? 8 : 64);
+    if (out_bytes < per * num_slices) return B2BU_ERR_ARGUMENT;
+    std::vector<SliceReq> slices(num_slices);
+    std::vector<ImageReq> images(num_slices);
+    for (uint32_t i = 0; i < num_slices; i++) {
+        if (slice_ofs[i] + slice_len[i] > data_len) return B2BU_ERR_RANGE;
+        slices[i] = {data + slice_ofs[i], slice_len[i], nbx, nby};
+        images[i] = {(int)i, -1, per * i};
+    }
+    return etc1s_run(h, target, slices, images, out, per * num_slices);
+}
+
+int b2bu_etc1s_transcode_to_etc1(b2bu_etc1s* h, uint32_t nbx, uint32_t nby, const uint8_t* slice, size_t slice_len, uint8_t* out, size_t out_bytes)
+{
+    const uint64_t ofs = 0, len = slice_len;
+    return b2bu_etc1s_transcode_slices(h, B2BU_ETC1, nbx, nby, slice, slice_len, &ofs, &len, 1, out, out_bytes);
+}
+
+int b2bu_etc1s_decode_to_rgba(b2bu_etc1s* h, uint32_t nbx, uint32_t nby, const uint8_t* rgb_slice, size_t rgb_len, const uint8_t* alpha_slice,
+                              size_t alpha_len, uint8_t* out, size_t out_bytes)
+{
+    if (!h || !rgb_slice || !out) return B2BU_ERR_ARGUMENT;
+    const uint64_t total = (uint64_t)nbx * nby * 64;
+    if (out_bytes < total) return B2BU_ERR_ARGUMENT;
+    std::vector<SliceReq> slices;
+    slices.push_back({rgb_slice, rgb_len, nbx, nby});
+    if (alpha_slice) slices.push_back({alpha_slice, alpha_len, nbx, nby});
+    std::vector<ImageReq> images(1);
+    images[0] = {0, alpha_slice ? 1 : -1, 0};
+    return etc1s_run(h, B2BU_RGBA, slices, images, out, total);
+}
+
+}  // extern "C"

@@ -1169,3 +1169,4 @@ ORC_API void orc_bc7_shared_pbits(unsigned comps, unsigned comp_bits, const uint
 }
 
 #include "basisu_oracle_etc1s.inc"
+#include "etc1s_encoder.inc"
