@@ -4,7 +4,7 @@
  * This is the drop-in boundary for the hot path of JakubValtar/basisu_rs.  The reference is a
  * pure-Rust library with no FFI of its own; each entry point below names the reference item it
  * replaces (paths relative to the reference crate root) and is what a `extern "C"` block in a
- * Rust shim would bind (see INTEGRATION.md and bindings/rust/).  Plain pointers and sizes only.
+ * Rust shim would bind.  Plain pointers and sizes only.
  *
  * Conventions
  *   - Every function returns a b2bu_status code (0 = OK).  b2bu_error_string() maps a code to the
