@@ -309,39 +309,153 @@ template <int M> B2BU_DI void unpack_endpoints(const uint4& b, const DevTables& 
     for (int i = 0; i < MD<M>::N; i++) e[i] = unquant<M>(T, d[i], m[i]);
 }
 
-// uastc.rs:237-327 decode_block_to_rgba for one (non void-extent) mode; px = 0xAABBGGRR, raster order
-template <int M> B2BU_DI void decode_rgba(const uint4& b, const DevTables& T, uint32_t pat, uint32_t compsel, uint32_t (&px)[16])
+// ------------------------------------------------------------------------------------------
+// uastc.rs:237-327 decode_block_to_rgba, split in two so that the expensive half is ONE piece of
+// code shared by every mode (instruction-cache footprint: the 18 specialised copies of the texel
+// loop were 150 KB and thrashed the 32 KB L1.5 I-cache):
+//   canon_front<M>   mode-specialised, small: endpoints -> packed pairs, weights -> one byte per
+//                    texel, already unquantised to 0..64 (SWAR on the whole weight stream)
+//   interp_rows<>    mode-independent: 16 texels of ASTC interpolation from the canonical block
+// ------------------------------------------------------------------------------------------
+struct Canon {
+    uint32_t lo_rb[3], hi_rb[3], lo_ga[3], hi_ga[3];   // endpoint pairs per subset: rb = R | B << 16, ga = G | A << 16
+    uint4 w0, w1;                                      // unquantised weights of plane 0 / 1, one byte per texel
+    uint32_t pw;                                       // subset map, 2 bits per texel
+    uint32_t mrb, mga;                                 // 16-bit lanes that take plane 1
+};
+
+// ASTC weight unquantisation (uastc.rs:697-719) on four byte lanes at once
+template <int WB> B2BU_DI uint32_t unquant_weight4(uint32_t w)
+{
+    uint32_t r;
+    if (WB == 1) return w << 6;                                        // 0 -> 0, 1 -> 63 + 1
+    else if (WB == 2) r = w * 21u;
+    else if (WB == 3) r = w * 9u;
+    else if (WB == 4) r = (w << 2) | ((w >> 2) & 0x03030303u);
+    else r = (w << 1) | ((w >> 4) & 0x01010101u);
+    return r + ((r >> 5) & 0x01010101u);
+}
+
+// four consecutive texels (4*j .. 4*j+3) of plane p of the uniform stream U -> four byte lanes
+template <int WB, int PLANES> B2BU_DI uint32_t weight_bytes4(const uint4& U, int j, int p)
+{
+    uint32_t t;
+    if (PLANES == 1) {
+        t = getbits(U, 4 * WB * j, 4 * WB);
+        if (WB == 2) { t = (t | (t << 12)) & 0x000F000Fu; t = (t | (t << 6)) & 0x03030303u; }
+        else if (WB == 3) { t = (t | (t << 10)) & 0x003F003Fu; t = (t | (t << 5)) & 0x07070707u; }
+        else if (WB == 4) { t = (t | (t << 8)) & 0x00FF00FFu; t = (t | (t << 4)) & 0x0F0F0F0Fu; }
+        else { t = (t & 0x3FFu) | ((t << 6) & 0x03FF0000u); t = (t & 0x001F001Fu) | ((t << 3) & 0x1F001F00u); }   // WB == 5
+    } else {
+        // texel-major, plane-minor: texel i of plane p sits at bit (2 * i + p) * WB
+        t = getbits(U, 8 * WB * j + p * WB, 8 * WB - WB);
+        if (WB == 1) { t &= 0x55u; t = (t | (t << 12)) & 0x00050005u; t = (t | (t << 6)) & 0x01010101u; }
+        else { t &= 0x3333u; t = (t | (t << 8)) & 0x00330033u; t = (t | (t << 4)) & 0x03030303u; }   // WB == 2
+    }
+    return unquant_weight4<WB>(t);
+}
+
+template <int M> B2BU_DI void canon_front(const uint4& b, const DevTables& T, uint32_t pat, uint32_t compsel, Canon& c)
 {
     using D = MD<M>;
     uint32_t e[D::N];
     unpack_endpoints<M>(b, T, e);
     Pairs<M> p;
     assemble_pairs<M>(e, p);
-    const uint4 U = uniform_weights<M>(b, T, pat);
-    const uint32_t pw = pattern_word<M>(T, pat);
-    uint32_t mrb = 0u, mga = 0u;
-    if (D::planes == 2) {
-        mrb = compsel == 0u ? 0x000000FFu : compsel == 2u ? 0x00FF0000u : 0u;
-        mga = compsel == 1u ? 0x000000FFu : compsel == 3u ? 0x00FF0000u : 0u;
-    }
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        uint32_t lrb = p.lo_rb[0], hrb = p.hi_rb[0], lga = p.lo_ga[0], hga = p.hi_ga[0];
-        if (D::subsets >= 2) {
-            const uint32_t s = (pw >> (2 * i)) & 3u;
-            if (s == 1u) { lrb = p.lo_rb[1]; hrb = p.hi_rb[1]; lga = p.lo_ga[1]; hga = p.hi_ga[1]; }
-            if (D::subsets == 3) if (s == 2u) { lrb = p.lo_rb[D::subsets - 1]; hrb = p.hi_rb[D::subsets - 1]; lga = p.lo_ga[D::subsets - 1]; hga = p.hi_ga[D::subsets - 1]; }
-        }
-        const uint32_t w0 = unquant_weight<D::wbits>(getbits(U, i * D::planes * D::wbits, D::wbits));
-        uint32_t rb = lerp2(lrb, hrb, w0), ga = lerp2(lga, hga, w0);
-        if (D::planes == 2) {
-            const uint32_t w1 = unquant_weight<D::wbits>(getbits(U, (i * 2 + 1) * D::wbits, D::wbits));
-            const uint32_t rb1 = lerp2(lrb, hrb, w1), ga1 = lerp2(lga, hga, w1);
-            rb = (rb & ~mrb) | (rb1 & mrb);
-            ga = (ga & ~mga) | (ga1 & mga);
-        }
-        px[i] = rb | (ga << 8);
+    for (int s = 0; s < 3; s++) {
+        const int q = s < D::subsets ? s : 0;
+        c.lo_rb[s] = p.lo_rb[q]; c.hi_rb[s] = p.hi_rb[q]; c.lo_ga[s] = p.lo_ga[q]; c.hi_ga[s] = p.hi_ga[q];
     }
+    const uint4 U = uniform_weights<M>(b, T, pat);
+    c.w0 = make_uint4(weight_bytes4<D::wbits, D::planes>(U, 0, 0), weight_bytes4<D::wbits, D::planes>(U, 1, 0),
+                      weight_bytes4<D::wbits, D::planes>(U, 2, 0), weight_bytes4<D::wbits, D::planes>(U, 3, 0));
+    if (D::planes == 2)
+        c.w1 = make_uint4(weight_bytes4<D::wbits, D::planes>(U, 0, 1), weight_bytes4<D::wbits, D::planes>(U, 1, 1),
+                          weight_bytes4<D::wbits, D::planes>(U, 2, 1), weight_bytes4<D::wbits, D::planes>(U, 3, 1));
+    else c.w1 = c.w0;
+    c.pw = pattern_word<M>(T, pat);
+    c.mrb = 0u; c.mga = 0u;
+    if (D::planes == 2) {
+        c.mrb = compsel == 0u ? 0x0000FFFFu : compsel == 2u ? 0xFFFF0000u : 0u;
+        c.mga = compsel == 1u ? 0x0000FFFFu : compsel == 3u ? 0xFFFF0000u : 0u;
+    }
+}
+
+// ((l*257)*(64-w) + (h*257)*w + 32) >> 14 on two 16-bit lanes, returned still shifted left by 6:
+// the caller takes bytes 0 and 2 of (result >> 6) with one byte permute
+B2BU_DI uint32_t lerp2_raw(uint32_t lo, uint32_t hi, uint32_t w, uint32_t iw)
+{
+    const uint32_t t = lo * iw + hi * w;
+    return t + (((t + 0x00200020u) >> 8) & 0x00FF00FFu);
+}
+
+// One row of four texels.  MULTI: more than one subset; DUAL: two weight planes.
+template <bool MULTI, bool DUAL>
+B2BU_DI uint4 interp_row(const Canon& c, uint32_t wr0, uint32_t wr1, uint32_t pwr)
+{
+    uint32_t px[4];
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        uint32_t lrb = c.lo_rb[0], hrb = c.hi_rb[0], lga = c.lo_ga[0], hga = c.hi_ga[0];
+        if (MULTI) {
+            const uint32_t s = (pwr >> (2 * x)) & 3u;
+            if (s == 1u) { lrb = c.lo_rb[1]; hrb = c.hi_rb[1]; lga = c.lo_ga[1]; hga = c.hi_ga[1]; }
+            if (s == 2u) { lrb = c.lo_rb[2]; hrb = c.hi_rb[2]; lga = c.lo_ga[2]; hga = c.hi_ga[2]; }
+        }
+        const uint32_t w = (wr0 >> (8 * x)) & 0xFFu, iw = 64u - w;
+        uint32_t rb = lerp2_raw(lrb, hrb, w, iw), ga = lerp2_raw(lga, hga, w, iw);
+        if (DUAL) {
+            const uint32_t v = (wr1 >> (8 * x)) & 0xFFu, iv = 64u - v;
+            const uint32_t rb1 = lerp2_raw(lrb, hrb, v, iv), ga1 = lerp2_raw(lga, hga, v, iv);
+            rb = (rb & ~c.mrb) | (rb1 & c.mrb);
+            ga = (ga & ~c.mga) | (ga1 & c.mga);
+        }
+        px[x] = __byte_perm(rb >> 6, ga >> 6, 0x6240);           // R, G, B, A
+    }
+    return make_uint4(px[0], px[1], px[2], px[3]);
+}
+
+// Row sinks: where the four pixel rows of a block go.  ROLLED sinks let the row loop stay a loop
+// (4x less code); the register-array sink needs it unrolled.
+struct PxArraySink {
+    static constexpr bool ROLLED = false;
+    uint32_t* px;
+    B2BU_DI void row(int y, const uint4& v) { px[4 * y] = v.x; px[4 * y + 1] = v.y; px[4 * y + 2] = v.z; px[4 * y + 3] = v.w; }
+};
+struct StridedRowSink {                    // rows `stride` uint4 apart (shared staging buffer or the global image)
+    static constexpr bool ROLLED = true;
+    uint4* p;
+    uint64_t stride;
+    B2BU_DI void row(int y, const uint4& v) { p[(uint64_t)y * stride] = v; }
+};
+
+template <bool MULTI, bool DUAL, class Sink> B2BU_DI void interp_rows(Canon& c, Sink& sink)
+{
+    if (Sink::ROLLED) {
+#pragma unroll 1
+        for (int y = 0; y < 4; y++) {
+            sink.row(y, interp_row<MULTI, DUAL>(c, c.w0.x, c.w1.x, c.pw));
+            c.w0.x = c.w0.y; c.w0.y = c.w0.z; c.w0.z = c.w0.w;
+            if (DUAL) { c.w1.x = c.w1.y; c.w1.y = c.w1.z; c.w1.z = c.w1.w; }
+            c.pw >>= 8;
+        }
+    } else {
+        sink.row(0, interp_row<MULTI, DUAL>(c, c.w0.x, c.w1.x, c.pw));
+        sink.row(1, interp_row<MULTI, DUAL>(c, c.w0.y, c.w1.y, c.pw >> 8));
+        sink.row(2, interp_row<MULTI, DUAL>(c, c.w0.z, c.w1.z, c.pw >> 16));
+        sink.row(3, interp_row<MULTI, DUAL>(c, c.w0.w, c.w1.w, c.pw >> 24));
+    }
+}
+
+constexpr uint32_t kMultiSubsetModes = (1u << 2) | (1u << 3) | (1u << 4) | (1u << 7) | (1u << 9) | (1u << 16);
+constexpr uint32_t kDualPlaneModes = (1u << 6) | (1u << 11) | (1u << 13) | (1u << 17);
+
+template <class Sink> B2BU_DI void interp_block(uint32_t mode, Canon& c, Sink& sink)
+{
+    if ((kDualPlaneModes >> mode) & 1u) interp_rows<false, true>(c, sink);
+    else if ((kMultiSubsetModes >> mode) & 1u) interp_rows<true, false>(c, sink);
+    else interp_rows<false, false>(c, sink);
 }
 
 // void-extent colour (uastc.rs:387-394): bits 5..36
@@ -969,16 +1083,23 @@ template <int M> B2BU_DI bool header_ok(const uint4& b, uint32_t& pat, uint32_t&
     return pat < (uint32_t)MD<M>::PCOUNT;          // uastc.rs:360-365
 }
 
-// mode = T.mode_lut[low 7 bits] (uastc.rs:329-341); 19 = invalid code
-template <int TARGET>
-B2BU_DI uint32_t transcode_mode(uint32_t mode, const uint4& b, const DevTables& T, BlockOut& o)
+// mode = T.mode_lut[low 7 bits] (uastc.rs:329-341); 19 = invalid code.
+// RGBA rows go to `sink` (TARGET == TGT_RGBA); the other targets fill o.v / o.etc.
+template <int TARGET, class Sink>
+B2BU_DI uint32_t transcode_mode_sink(uint32_t mode, const uint4& b, const DevTables& T, BlockOut& o, Sink& sink)
 {
     uint32_t pat = 0, compsel = 0;
     if (mode == 8u) {
         const uint32_t c = mode8_rgba(b);
         if (TARGET == TGT_RGBA) {
+            const uint4 r = make_uint4(c, c, c, c);
+            if (Sink::ROLLED) {
+#pragma unroll 1
+                for (int y = 0; y < 4; y++) sink.row(y, r);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 16; i++) o.px[i] = c;
+                for (int y = 0; y < 4; y++) sink.row(y, r);
+            }
         } else if (TARGET == TGT_ASTC) o.v = astc_void_extent(c);
         else if (TARGET == TGT_BC7) o.v = bc7_void_extent(c, T);
         else {
@@ -997,21 +1118,33 @@ B2BU_DI uint32_t transcode_mode(uint32_t mode, const uint4& b, const DevTables& 
         }
         return ERR_OK;
     }
-    // RGBA, ETC1, ETC2: decode the texels once, then (for ETC) run the mode-independent packer
+    // RGBA, ETC1, ETC2: mode-specialised front-end to the canonical block, then shared texel code
     EtcFlags f;
+    Canon c;
     switch (mode) {
 #define X(M) case M: if (!header_ok<M>(b, pat, compsel)) return ERR_PATTERN; \
                      if (TARGET != TGT_RGBA) f = read_trans_flags<M>(b); \
-                     decode_rgba<M>(b, T, pat, compsel, o.px); break;
+                     canon_front<M>(b, T, pat, compsel, c); break;
         B2BU_FOR_EACH_MODE(X)
 #undef X
     default: return ERR_MODE;
     }
-    if (TARGET == TGT_ETC1 || TARGET == TGT_ETC2) {
+    if (TARGET == TGT_RGBA) {
+        interp_block(mode, c, sink);
+    } else {
+        PxArraySink ps{o.px};
+        interp_block(mode, c, ps);
         o.etc = etc1_block(o.px, f, T);
         if (TARGET == TGT_ETC2) { const uint2 a = etc2_alpha_block(o.px, f.etc2tm, T); o.v = make_uint4(a.x, a.y, o.etc.x, o.etc.y); }
     }
     return ERR_OK;
+}
+
+template <int TARGET>
+B2BU_DI uint32_t transcode_mode(uint32_t mode, const uint4& b, const DevTables& T, BlockOut& o)
+{
+    PxArraySink ps{o.px};
+    return transcode_mode_sink<TARGET>(mode, b, T, o, ps);
 }
 
 template <int TARGET>

@@ -8,24 +8,10 @@
 namespace b2bu {
 
 constexpr int kMaxDevicesK = 16;
-constexpr uint64_t kSortedMinBlocks = 2048;   // below this the sort cannot pay for itself
-
-// tile shape of the mode-sorted kernel (overridable for tuning runs: -DB2BU_TILE=... etc.)
-#ifndef B2BU_TILE
-#define B2BU_TILE 2048
+#ifndef B2BU_SORT_MIN
+#define B2BU_SORT_MIN 2048
 #endif
-#ifndef B2BU_THREADS
-#define B2BU_THREADS 512
-#endif
-#ifndef B2BU_CTAS_ASTC
-#define B2BU_CTAS_ASTC 3
-#endif
-#ifndef B2BU_DYN_ASTC
-#define B2BU_DYN_ASTC 0
-#endif
-#ifndef B2BU_CTAS_OTHER
-#define B2BU_CTAS_OTHER 2
-#endif
+constexpr uint64_t kSortedMinBlocks = B2BU_SORT_MIN;   // below this the sort cannot pay for itself
 
 __device__ DevTables g_tables;
 static const DevTables h_tables =
@@ -80,36 +66,42 @@ __global__ void __launch_bounds__(256) uastc_transcode_kernel(const uint4* __res
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nblocks; i += stride) {
         const uint4 b = __ldg(in + i);
         BlockOut o;
-        const uint32_t e = transcode_one<TARGET>(b, T, o);
+        // uastc.rs:96-106: row-major image, pitch 4*blocks_per_row pixels
+        const uint64_t bx = i % blocks_per_row, by = i / blocks_per_row;
+        StridedRowSink sink{reinterpret_cast<uint4*>(out) + (by * 4) * blocks_per_row + bx, (uint64_t)blocks_per_row};
+        const uint32_t e = transcode_mode_sink<TARGET>(T.mode_lut[b.x & 127u], b, T, o, sink);
         if (e != ERR_OK) {
             report_error(err, index_base + i, e);
             o.v = make_uint4(0u, 0u, 0u, 0u); o.etc = make_uint2(0u, 0u);
-#pragma unroll
-            for (int k = 0; k < 16; k++) o.px[k] = 0u;
+            if (TARGET == TGT_RGBA) {
+#pragma unroll 1
+                for (int y = 0; y < 4; y++) sink.row(y, make_uint4(0u, 0u, 0u, 0u));
+            }
         }
-        if (TARGET == TGT_RGBA) {
-            // uastc.rs:96-106: row-major image, pitch 4*blocks_per_row pixels
-            const uint64_t bx = i % blocks_per_row, by = i / blocks_per_row;
-            uint4* dst = reinterpret_cast<uint4*>(out) + (by * 4) * blocks_per_row + bx;
-#pragma unroll
-            for (int y = 0; y < 4; y++) dst[(uint64_t)y * blocks_per_row] = make_uint4(o.px[4 * y], o.px[4 * y + 1], o.px[4 * y + 2], o.px[4 * y + 3]);
-        } else if (TARGET == TGT_ETC1) {
-            reinterpret_cast<uint2*>(out)[i] = o.etc;
-        } else {
-            reinterpret_cast<uint4*>(out)[i] = o.v;
-        }
+        if (TARGET == TGT_ETC1) reinterpret_cast<uint2*>(out)[i] = o.etc;
+        else if (TARGET != TGT_RGBA) reinterpret_cast<uint4*>(out)[i] = o.v;
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Mode-sorted tile kernel.  A warp that holds 32 consecutive blocks of a real texture sees many
-// different UASTC modes, and the mode-specialised code above would then run one mode at a time
-// with most lanes idle (measured: 2.4 of 32 lanes active on a shuffled payload).  So a CTA takes a
-// tile of TILE consecutive blocks, counting-sorts the block indices by mode in shared memory
-// (warp-aggregated with match.any), and its warps then pull 32-block work items that are
-// mode-uniform.  Results go back to the block's original slot in a shared staging buffer and
-// leave with fully coalesced 128-bit stores.  Bins are padded to 32, so lane occupancy is
-// TILE / (TILE + ~16 per mode present).
+// Mode-sorted, warp-specialised, persistent tile pipeline (one CTA per SM).
+//
+// Mode-specialised code diverges 19 ways inside a warp on real data and its instruction footprint
+// (46-190 KB) thrashes the 32 KB L1.5 instruction cache when every warp of an SM runs a different
+// mode.  So each CTA walks a contiguous range of blocks in tiles and runs three roles concurrently:
+//
+//   DMA warp (1 lane)   TMA bulk load of tile k+1 into the free slot, bulk store of finished tiles
+//   sorter warps        classify tile k+1 by UASTC mode, counting-sort the block indices into
+//                       mode bins padded to 32 (per-warp shared histograms, no CTA barrier)
+//   worker warps        pull 32-block, mode-uniform work items of tile k in bin order (heavy modes
+//                       first) and run the specialised transcode.  All workers of the SM are inside
+//                       the same few modes at any time, which keeps the hot code I-cache resident.
+//
+// The roles are connected by mbarriers per slot (full -> sorted -> done -> free); there is no
+// __syncthreads in the steady state and workers run on from tile k into tile k+1 without waiting
+// for each other.  16-byte results overwrite the block's own input slot in shared memory and leave
+// with one bulk store per tile; ETC1 (8 B) and RGBA (64 B, stored as four pixel rows per block row)
+// are staged in a second buffer so that every global write is a full-line bulk store.
 // ------------------------------------------------------------------------------------------
 constexpr int kBins = 20;                       // modes 0..18 + the invalid code (19)
 // processing order of the bins: roughly by decreasing per-block cost (endpoint count, trits/quints, subsets)
@@ -125,6 +117,10 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
@@ -143,200 +139,257 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes)
+__device__ __forceinline__ void tma_store_1d_nocommit(void* gmem_dst, const void* smem_src, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
-template <int TARGET> struct SortedCfg {
-    static constexpr int TILE = B2BU_TILE;
-    static constexpr int THREADS = B2BU_THREADS;
-    static constexpr int PER = TILE / THREADS;
+#ifndef B2BU_TILE16
+#define B2BU_TILE16 4096
+#endif
+#ifndef B2BU_TILE_RGBA
+#define B2BU_TILE_RGBA 1024
+#endif
+#ifndef B2BU_SORT_WARPS
+#define B2BU_SORT_WARPS 4
+#endif
+#ifndef B2BU_WORK_WARPS
+#define B2BU_WORK_WARPS 27
+#endif
+
+template <int TARGET> struct PipeCfg {
     static constexpr int OB = TARGET == TGT_RGBA ? 64 : TARGET == TGT_ETC1 ? 8 : 16;
-    // ASTC / BC7 / ETC2 results overwrite the block's own 16-byte input slot (read once by the same
-    // thread just before) and leave with one bulk store; ETC1 (8 B) is staged compactly in a second
-    // buffer; RGBA (64 B) is written straight to global memory by the lane that decoded it.
     static constexpr bool IN_PLACE = OB == 16;
-    static constexpr bool TMA_STORE = OB <= 16;
-    static constexpr int CTAS_PER_SM = TARGET == TGT_ASTC ? B2BU_CTAS_ASTC : B2BU_CTAS_OTHER;
-    // work-item scheduling inside a tile: ASTC items are short and even, a static round-robin beats the
-    // shared counter; the heavier, more uneven targets (BC7, RGBA, ETC) gain from dynamic pulls
-    static constexpr bool DYNAMIC = TARGET != TGT_ASTC || B2BU_DYN_ASTC;
+    static constexpr int TILE = TARGET == TGT_RGBA ? B2BU_TILE_RGBA : B2BU_TILE16;
+    static constexpr int SORT_WARPS = B2BU_SORT_WARPS;
+    static constexpr int SORT_THREADS = SORT_WARPS * 32;
+    static constexpr int WORK_WARPS = B2BU_WORK_WARPS;
+    static constexpr int THREADS = 32 * (1 + SORT_WARPS + WORK_WARPS);
+    static constexpr int PERS = (TILE + SORT_THREADS - 1) / SORT_THREADS;     // blocks per sorter thread
     static constexpr int MAXORD = TILE + kBins * 32;
     static constexpr int MAXITEMS = MAXORD / 32;
-    static constexpr size_t OFF_IN = (TableBytes<TARGET>::value + 127) / 128 * 128;   // two input buffers (double buffered)
-    static constexpr size_t OFF_OUT = OFF_IN + 2 * (size_t)TILE * 16;       // ETC1 staging only
-    static constexpr size_t OFF_ORDER = OFF_OUT + (TARGET == TGT_ETC1 ? (size_t)TILE * 8 : 0);
-    static constexpr size_t OFF_IMODE = OFF_ORDER + (size_t)MAXORD * 2;
-    static constexpr size_t OFF_CNT = (OFF_IMODE + MAXITEMS + 15) / 16 * 16;
-    static constexpr size_t OFF_BAR = OFF_CNT + 4 * (32 + 32 + 4);
-    static constexpr size_t SMEM = OFF_BAR + 16;
+    static constexpr size_t OFF_IN = (TableBytes<TARGET>::value + 127) / 128 * 128;   // two slots
+    static constexpr size_t OFF_OUT = OFF_IN + 2 * (size_t)TILE * 16;                  // staging for ETC1 / RGBA, two slots
+    static constexpr size_t OUT_SLOT = IN_PLACE ? 0 : (size_t)TILE * OB;
+    static constexpr size_t OFF_ORDER = OFF_OUT + 2 * OUT_SLOT;
+    static constexpr size_t OFF_INFO = OFF_ORDER + 2 * (size_t)MAXORD * 2;
+    static constexpr size_t OFF_WCNT = (OFF_INFO + 2 * (size_t)MAXITEMS * 2 + 15) / 16 * 16;
+    static constexpr size_t OFF_BASE = OFF_WCNT + (size_t)SORT_WARPS * 32 * 4;
+    static constexpr size_t OFF_CTL = OFF_BASE + (size_t)SORT_WARPS * 32 * 4;
+    static constexpr size_t OFF_BAR = OFF_CTL + 2 * 4 * 4;
+    static constexpr size_t SMEM = OFF_BAR + 6 * 8;
+    static_assert(SMEM <= 227 * 1024, "tile configuration does not fit shared memory");
+    static_assert(THREADS <= 1024, "too many warps");
 };
 
+// contiguous, 32-block aligned share of CTA c out of G
+__device__ __forceinline__ uint64_t cta_range_start(uint64_t nblocks, uint32_t c, uint32_t G)
+{
+    if (c >= G) return nblocks;
+    return ((nblocks / G) * c + (nblocks % G) * c / G) & ~31ull;
+}
+
 template <int TARGET>
-__global__ void __launch_bounds__(SortedCfg<TARGET>::THREADS, SortedCfg<TARGET>::CTAS_PER_SM)
+__global__ void __launch_bounds__(PipeCfg<TARGET>::THREADS, 1)
 uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64_t nblocks, uint32_t blocks_per_row,
                     uint64_t index_base, unsigned long long* __restrict__ err)
 {
-    using C = SortedCfg<TARGET>;
+    using C = PipeCfg<TARGET>;
     extern __shared__ __align__(128) unsigned char smem[];
     DevTables& T = *reinterpret_cast<DevTables*>(smem);
-    uint4* xbuf = reinterpret_cast<uint4*>(smem + C::OFF_IN);
-    unsigned char* out_s = smem + C::OFF_OUT;
-    uint16_t* order = reinterpret_cast<uint16_t*>(smem + C::OFF_ORDER);
-    uint8_t* item_mode = smem + C::OFF_IMODE;
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + C::OFF_CNT);
-    uint32_t* offs = cnt + 32;
-    uint32_t* ctl = offs + 32;                   // [0] next work item, [1] number of work items
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint4* in_s = reinterpret_cast<uint4*>(smem + C::OFF_IN);                 // [2][TILE]
+    unsigned char* out_s = smem + C::OFF_OUT;                                 // [2][OUT_SLOT]
+    uint16_t* order = reinterpret_cast<uint16_t*>(smem + C::OFF_ORDER);       // [2][MAXORD]
+    uint16_t* info = reinterpret_cast<uint16_t*>(smem + C::OFF_INFO);         // [2][MAXITEMS]: mode | lanes << 8
+    uint32_t* wcnt = reinterpret_cast<uint32_t*>(smem + C::OFF_WCNT);         // [SORT_WARPS][32]
+    uint32_t* wbase = reinterpret_cast<uint32_t*>(smem + C::OFF_BASE);        // [SORT_WARPS][32]
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(smem + C::OFF_CTL);           // [2][4]: next item, number of items
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);          // full[2], sorted[2], done[2]
+    uint64_t* bar_full = bars, *bar_sorted = bars + 2, *bar_done = bars + 4;
 
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint64_t ntiles = (nblocks + C::TILE - 1) / C::TILE;
-    auto tile_blocks = [&](uint64_t t) -> uint32_t {
-        const uint64_t rem = nblocks - t * C::TILE;
-        return (uint32_t)(rem < (uint64_t)C::TILE ? rem : (uint64_t)C::TILE);
-    };
-    if (tid < 32) cnt[tid] = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // this CTA's contiguous block range, cut into equal tiles of at most TILE blocks (multiples of 32)
+    const uint64_t r0 = cta_range_start(nblocks, blockIdx.x, gridDim.x);
+    const uint64_t r1 = cta_range_start(nblocks, blockIdx.x + 1, gridDim.x);
+    const uint32_t rlen = (uint32_t)(r1 - r0);
+    const uint32_t ntiles = (rlen + C::TILE - 1) / C::TILE;
+    const uint32_t tsz = ntiles ? (((rlen + ntiles - 1) / ntiles + 31u) & ~31u) : 0u;
+    auto tile_blocks = [&](uint32_t k) -> uint32_t { const uint32_t o = k * tsz; return rlen - o < tsz ? rlen - o : tsz; };
+
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
+        mbar_init(&bar_sorted[0], 1); mbar_init(&bar_sorted[1], 1);
+        mbar_init(&bar_done[0], C::WORK_WARPS); mbar_init(&bar_done[1], C::WORK_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     load_tables(&T, TableBytes<TARGET>::value);  // ends with __syncthreads()
-    if (tid == 0) {                              // prologue: first tile -> buffer 0
-        const uint64_t t0 = blockIdx.x;
-        const uint32_t bytes = tile_blocks(t0) * 16u;
-        mbar_expect_tx(&bars[0], bytes);
-        tma_load_1d(xbuf, in + t0 * C::TILE, bytes, &bars[0]);
+
+    if (warp == 0) {
+        // ================================ DMA warp ================================
+        if (lane != 0) return;
+        auto store_tile = [&](uint32_t k) {
+            const uint32_t s = k & 1u, nt = tile_blocks(k);
+            const uint64_t g0 = r0 + (uint64_t)k * tsz;
+            fence_async_smem();
+            if (TARGET == TGT_RGBA) {
+                // four pixel rows per block row; a tile may span several block rows
+                const uint4* src = reinterpret_cast<const uint4*>(out_s + s * C::OUT_SLOT);   // [4][TILE]
+                uint32_t i = 0;
+                uint64_t by = g0 / blocks_per_row;
+                uint32_t bx = (uint32_t)(g0 - by * blocks_per_row);
+                while (i < nt) {
+                    const uint32_t seg = nt - i < blocks_per_row - bx ? nt - i : blocks_per_row - bx;
+#pragma unroll
+                    for (int y = 0; y < 4; y++)
+                        tma_store_1d_nocommit(reinterpret_cast<uint4*>(out) + (by * 4 + y) * blocks_per_row + bx, src + y * C::TILE + i, seg * 16u);
+                    i += seg; bx = 0; by++;
+                }
+            } else if (TARGET == TGT_ETC1) {
+                const uint2* src = reinterpret_cast<const uint2*>(out_s + s * C::OUT_SLOT);
+                uint2* dst = reinterpret_cast<uint2*>(out) + g0;
+                if (nt >> 1) tma_store_1d_nocommit(dst, src, (nt >> 1) * 16u);
+                if (nt & 1u) dst[nt - 1] = src[nt - 1];          // bulk copies move multiples of 16 bytes
+            } else {
+                tma_store_1d_nocommit(reinterpret_cast<uint4*>(out) + g0, in_s + s * C::TILE, nt * 16u);
+            }
+            tma_store_commit();
+        };
+        for (uint32_t k = 0; k < ntiles; k++) {
+            const uint32_t s = k & 1u, u = k >> 1;
+            if (k >= 2) {                                      // slot reuse: tile k-2 must be finished and stored
+                mbar_wait(&bar_done[s], (u - 1u) & 1u);
+                store_tile(k - 2);
+                tma_store_wait_read();
+            }
+            const uint32_t bytes = tile_blocks(k) * 16u;
+            mbar_expect_tx(&bar_full[s], bytes);
+            tma_load_1d(in_s + s * C::TILE, in + r0 + (uint64_t)k * tsz, bytes, &bar_full[s]);
+        }
+        for (uint32_t k = ntiles >= 2 ? ntiles - 2 : 0; k < ntiles; k++) {
+            mbar_wait(&bar_done[k & 1u], (k >> 1) & 1u);
+            store_tile(k);
+        }
+        tma_store_wait_all();
+        return;
     }
 
-    uint32_t it = 0;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-        const uint32_t cur = it & 1u;
-        uint4* in_s = xbuf + cur * C::TILE;
-        const uint64_t base = tile * C::TILE;
-        const uint32_t nt = tile_blocks(tile);
-        const uint32_t bx0 = TARGET == TGT_RGBA ? (uint32_t)(base % blocks_per_row) : 0u;
-        const uint64_t by0 = TARGET == TGT_RGBA ? base / blocks_per_row : 0u;
-
-        // ---- A: wait for the tile, classify, rank inside each mode bin ----
-        for (int i = tid; i < C::MAXORD / 8; i += C::THREADS) reinterpret_cast<uint4*>(order)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
-        mbar_wait(&bars[cur], (it >> 1) & 1u);
-        uint32_t mymode[C::PER], mypos[C::PER];
+    if (warp <= C::SORT_WARPS) {
+        // ================================ sorter warps ================================
+        const int sw = warp - 1, st = tid - 32;
+        uint32_t* mycnt = wcnt + sw * 32;
+        for (uint32_t k = 0; k < ntiles; k++) {
+            const uint32_t s = k & 1u, u = k >> 1, nt = tile_blocks(k);
+            const uint4* tin = in_s + s * C::TILE;
+            mycnt[lane] = 0;
+            __syncwarp();
+            mbar_wait(&bar_full[s], u & 1u);
+            // A: classify, rank inside (warp, mode)
+            uint32_t mr[C::PERS];
 #pragma unroll
-        for (int k = 0; k < C::PER; k++) {
-            const uint32_t idx = tid + k * C::THREADS;
-            mymode[k] = idx < nt ? (uint32_t)T.mode_lut[in_s[idx].x & 127u] : 31u;
-        }
-#pragma unroll
-        for (int k = 0; k < C::PER; k++) {
-            const uint32_t m = mymode[k];
-            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, m);
-            const int leader = __ffs(peers) - 1;
-            uint32_t p0 = 0;
-            if (lane == leader && m < (uint32_t)kBins) p0 = atom_add_shared(&cnt[m], __popc(peers));
-            p0 = __shfl_sync(0xFFFFFFFFu, p0, leader);
-            mypos[k] = p0 + __popc(peers & ((1u << lane) - 1u));
-        }
-        __syncthreads();
-        // ---- B: bin offsets (each bin padded to a multiple of 32) and the item -> mode map ----
-        if (tid < 32) {
-            // bins are laid out heaviest mode first so that the dynamic pulls end with the cheap items
-            const uint32_t bin = tid < kBins ? (uint32_t)kBinOrder[tid] : 31u;
-            const uint32_t c = tid < kBins ? cnt[bin] : 0u;
-            const uint32_t padded = (c + 31u) & ~31u;
-            uint32_t incl = padded;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += v; }
-            const uint32_t excl = incl - padded;
-            offs[bin] = excl;
-            for (uint32_t j = excl >> 5; j < (incl >> 5); j++) item_mode[j] = (uint8_t)bin;
-            cnt[bin] = 0;
-            if (tid == 31) { ctl[0] = 0; ctl[1] = incl >> 5; }
-        }
-        __syncthreads();
-        // ---- C: scatter block indices into their bins ----
-#pragma unroll
-        for (int k = 0; k < C::PER; k++)
-            if (mymode[k] < (uint32_t)kBins) order[offs[mymode[k]] + mypos[k]] = (uint16_t)(tid + k * C::THREADS);
-        // prefetch the next tile into the other buffer while this one is transcoded
-        if (tid == 0 && tile + gridDim.x < ntiles) {
-            if (C::TMA_STORE) tma_store_wait_read();     // the bulk store that last read that buffer has drained
-            const uint64_t tn = tile + gridDim.x;
-            const uint32_t bytes = tile_blocks(tn) * 16u;
-            mbar_expect_tx(&bars[cur ^ 1u], bytes);
-            tma_load_1d(xbuf + (cur ^ 1u) * C::TILE, in + tn * C::TILE, bytes, &bars[cur ^ 1u]);
-        } else if (tid == 0 && TARGET == TGT_ETC1) {
-            tma_store_wait_read();                        // ETC1 staging buffer is single: previous store must have read it
-        }
-        __syncthreads();
-        // ---- D: warps take mode-uniform work items ----
-        const uint32_t nitems = ctl[1];
-        for (uint32_t wi = tid >> 5;; wi += C::THREADS / 32) {
-            uint32_t item = wi;
-            if (C::DYNAMIC) {
-                if (lane == 0) item = atom_add_shared(&ctl[0], 1u);
-                item = __shfl_sync(0xFFFFFFFFu, item, 0);
+            for (int j = 0; j < C::PERS; j++) {
+                const uint32_t idx = st + j * C::SORT_THREADS;
+                uint32_t m = 31u, rank = 0u;
+                if (idx < nt) {
+                    m = T.mode_lut[tin[idx].x & 127u];
+                    rank = atom_add_shared(&mycnt[m], 1u);
+                }
+                mr[j] = m | (rank << 8);
             }
+            named_bar_sync(1, C::SORT_THREADS);
+            // B: bin offsets (each bin padded to a multiple of 32, heaviest mode first), item table
+            if (sw == 0) {
+                const uint32_t bin = lane < kBins ? (uint32_t)kBinOrder[lane] : 31u;
+                uint32_t c = 0;
+                if (lane < kBins) {
+#pragma unroll
+                    for (int w = 0; w < C::SORT_WARPS; w++) { wbase[w * 32 + bin] = c; c += wcnt[w * 32 + bin]; }
+                }
+                const uint32_t padded = (c + 31u) & ~31u;
+                uint32_t incl = padded;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += v; }
+                const uint32_t excl = incl - padded;
+                if (lane < kBins) {
+#pragma unroll
+                    for (int w = 0; w < C::SORT_WARPS; w++) wbase[w * 32 + bin] += excl;
+                    for (uint32_t j = 0; j < (padded >> 5); j++) {
+                        const uint32_t lanes = c - 32u * j < 32u ? c - 32u * j : 32u;
+                        info[s * C::MAXITEMS + (excl >> 5) + j] = (uint16_t)(bin | (lanes << 8));
+                    }
+                }
+                if (lane == 31) { ctl[s * 4 + 0] = 0; ctl[s * 4 + 1] = incl >> 5; }
+            }
+            named_bar_sync(1, C::SORT_THREADS);
+            // C: scatter block indices into their bins
+            const uint32_t* mybase = wbase + sw * 32;
+            uint16_t* ord = order + s * C::MAXORD;
+#pragma unroll
+            for (int j = 0; j < C::PERS; j++) {
+                const uint32_t m = mr[j] & 0xFFu;
+                if (m < (uint32_t)kBins) ord[mybase[m] + (mr[j] >> 8)] = (uint16_t)(st + j * C::SORT_THREADS);
+            }
+            named_bar_sync(1, C::SORT_THREADS);
+            if (st == 0) mbar_arrive(&bar_sorted[s]);
+        }
+        return;
+    }
+
+    // ================================ worker warps ================================
+    for (uint32_t k = 0; k < ntiles; k++) {
+        const uint32_t s = k & 1u, u = k >> 1;
+        uint4* tin = in_s + s * C::TILE;
+        unsigned char* tout = out_s + s * C::OUT_SLOT;
+        const uint16_t* ord = order + s * C::MAXORD;
+        const uint16_t* inf = info + s * C::MAXITEMS;
+        const uint64_t base = r0 + (uint64_t)k * tsz;
+        mbar_wait(&bar_sorted[s], u & 1u);
+        mbar_wait(&bar_full[s], u & 1u);          // completed long ago: observes the bulk-copied bytes directly
+        const uint32_t nitems = ctl[s * 4 + 1];
+        for (;;) {
+            uint32_t item = 0;
+            if (lane == 0) item = atom_add_shared(&ctl[s * 4 + 0], 1u);
+            item = __shfl_sync(0xFFFFFFFFu, item, 0);
             if (item >= nitems) break;
-            const uint32_t mode = item_mode[item];
-            const uint32_t idx = order[item * 32 + lane];
-            if (idx != 0xFFFFu) {
-                const uint4 b = in_s[idx];
+            const uint32_t inf_w = inf[item];
+            const uint32_t mode = inf_w & 0xFFu;
+            if ((uint32_t)lane < (inf_w >> 8)) {
+                const uint32_t idx = ord[item * 32 + lane];
+                const uint4 b = tin[idx];
                 BlockOut o;
-                const uint32_t e = transcode_mode<TARGET>(mode, b, T, o);
+                StridedRowSink sink{reinterpret_cast<uint4*>(tout) + idx, (uint64_t)C::TILE};     // RGBA: [4][TILE] pixel rows
+                const uint32_t e = transcode_mode_sink<TARGET>(mode, b, T, o, sink);
                 if (e != ERR_OK) {
                     report_error(err, index_base + base + idx, e);
                     o.v = make_uint4(0u, 0u, 0u, 0u); o.etc = make_uint2(0u, 0u);
-#pragma unroll
-                    for (int k = 0; k < 16; k++) o.px[k] = 0u;
+                    if (TARGET == TGT_RGBA) {
+#pragma unroll 1
+                        for (int y = 0; y < 4; y++) sink.row(y, make_uint4(0u, 0u, 0u, 0u));
+                    }
                 }
-                if (TARGET == TGT_RGBA) {
-                    // uastc.rs:96-106: row-major image, pitch 4*blocks_per_row pixels; four 16-byte row stores
-                    const uint32_t t = bx0 + idx;                       // 32-bit: bx0 < blocks_per_row, idx < TILE
-                    const uint64_t by = by0 + t / blocks_per_row;
-                    const uint32_t bx = t % blocks_per_row;
-                    uint4* p = reinterpret_cast<uint4*>(out) + (by * 4) * blocks_per_row + bx;
-#pragma unroll
-                    for (int y = 0; y < 4; y++) p[(uint64_t)y * blocks_per_row] = make_uint4(o.px[4 * y], o.px[4 * y + 1], o.px[4 * y + 2], o.px[4 * y + 3]);
-                } else if (TARGET == TGT_ETC1) {
-                    reinterpret_cast<uint2*>(out_s)[idx] = o.etc;
-                } else {
-                    in_s[idx] = o.v;
-                }
+                if (TARGET == TGT_ETC1) reinterpret_cast<uint2*>(tout)[idx] = o.etc;
+                else if (TARGET != TGT_RGBA) tin[idx] = o.v;
             }
         }
-        // ---- E: one bulk store per tile ----
-        if (C::TMA_STORE) {
-            fence_async_smem();                          // make the generic-proxy writes visible to the async proxy
-            __syncthreads();
-            if (tid == 0) {
-                if (TARGET == TGT_ETC1) {
-                    if ((nt & 1u) == 0u) tma_store_1d(reinterpret_cast<uint2*>(out) + base, out_s, nt * 8u);
-                } else {
-                    tma_store_1d(reinterpret_cast<uint4*>(out) + base, in_s, nt * 16u);
-                }
-            }
-            if (TARGET == TGT_ETC1 && (nt & 1u)) {       // odd tail: bulk copies need multiples of 16 bytes
-                uint2* dst = reinterpret_cast<uint2*>(out) + base;
-                for (uint32_t i = tid; i < nt; i += C::THREADS) dst[i] = reinterpret_cast<const uint2*>(out_s)[i];
-            }
-        } else {
-            __syncthreads();                             // RGBA: in_s / order are reused by the next tile
-        }
+        fence_async_smem();                       // generic-proxy writes -> visible to the bulk store
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_done[s]);
     }
-    if (C::TMA_STORE && tid == 0) tma_store_wait_all();
 }
 
 template <int TARGET>
 static cudaError_t launch_sorted(const uint4* in, void* d_out, uint64_t nblocks, uint32_t bpr, uint64_t index_base,
                                  unsigned long long* d_err, int sm_count, cudaStream_t stream)
 {
-    using C = SortedCfg<TARGET>;
+    using C = PipeCfg<TARGET>;
     static bool configured[kMaxDevicesK] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -345,9 +398,9 @@ static cudaError_t launch_sorted(const uint4* in, void* d_out, uint64_t nblocks,
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    const uint64_t ntiles = (nblocks + C::TILE - 1) / C::TILE;
-    const uint64_t cap = (uint64_t)sm_count * C::CTAS_PER_SM;
-    const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+    // one persistent CTA per SM; fewer when the input is small (at least ~one half tile each)
+    const uint64_t want = (nblocks + C::TILE / 2 - 1) / (C::TILE / 2);
+    const unsigned grid = (unsigned)(want < (uint64_t)sm_count ? want : (uint64_t)sm_count);
     uastc_sorted_kernel<TARGET><<<grid, C::THREADS, C::SMEM, stream>>>(in, d_out, nblocks, bpr, index_base, d_err);
     return cudaGetLastError();
 }
