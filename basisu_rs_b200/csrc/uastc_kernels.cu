@@ -45,7 +45,7 @@ __device__ __forceinline__ uint32_t atom_add_shared(uint32_t* p, uint32_t v)
 {
     uint32_t old;
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v));
     return old;
 }
 
@@ -159,10 +159,20 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads)
 #define B2BU_TILE_RGBA 1024
 #endif
 #ifndef B2BU_SORT_WARPS
-#define B2BU_SORT_WARPS 4
+#define B2BU_SORT_WARPS 8
 #endif
 #ifndef B2BU_WORK_WARPS
-#define B2BU_WORK_WARPS 27
+#define B2BU_WORK_WARPS 23
+#endif
+
+#ifdef B2BU_TRACE
+// tuning aid (never in the product build): per-CTA clock64 time stamps of the pipeline hand-offs
+__device__ unsigned long long g_trace[160][64];
+#define TRACE(slot) do { if ((slot) < 64) g_trace[blockIdx.x][(slot)] = clock64(); } while (0)
+#define TRACE_ADD(slot, v) do { g_trace[blockIdx.x][(slot)] += (v); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#define TRACE_ADD(slot, v) do { } while (0)
 #endif
 
 template <int TARGET> struct PipeCfg {
@@ -221,9 +231,21 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
     const uint64_t r0 = cta_range_start(nblocks, blockIdx.x, gridDim.x);
     const uint64_t r1 = cta_range_start(nblocks, blockIdx.x + 1, gridDim.x);
     const uint32_t rlen = (uint32_t)(r1 - r0);
-    const uint32_t ntiles = (rlen + C::TILE - 1) / C::TILE;
-    const uint32_t tsz = ntiles ? (((rlen + ntiles - 1) / ntiles + 31u) & ~31u) : 0u;
-    auto tile_blocks = [&](uint32_t k) -> uint32_t { const uint32_t o = k * tsz; return rlen - o < tsz ? rlen - o : tsz; };
+    // tile k covers [tile_start(k), tile_start(k + 1)) of the range.  The first two tiles are short (TILE/4, TILE/2)
+    // so that the workers start early; the rest of the range is cut into equal tiles of at most TILE blocks.
+    const uint32_t a0 = rlen < (uint32_t)C::TILE / 4 ? rlen : (uint32_t)C::TILE / 4;
+    const uint32_t a1 = rlen - a0 < (uint32_t)C::TILE / 2 ? rlen - a0 : (uint32_t)C::TILE / 2;
+    const uint32_t rest = rlen - a0 - a1;
+    const uint32_t nrest = (rest + C::TILE - 1) / C::TILE;
+    const uint32_t tsz = nrest ? (((rest + nrest - 1) / nrest + 31u) & ~31u) : 0u;
+    const uint32_t ntiles = (a0 ? 1u : 0u) + (a1 ? 1u : 0u) + nrest;
+    auto tile_start = [&](uint32_t k) -> uint32_t {
+        if (k == 0) return 0u;
+        if (k == 1) return a0;
+        const uint32_t o = a0 + a1 + (k - 2) * tsz;
+        return o < rlen ? o : rlen;
+    };
+    auto tile_blocks = [&](uint32_t k) -> uint32_t { return tile_start(k + 1) - tile_start(k); };
 
     if (tid == 0) {
         mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
@@ -232,13 +254,14 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     load_tables(&T, TableBytes<TARGET>::value);  // ends with __syncthreads()
+    if (tid == 0) TRACE(60);
 
-    if (warp == 0) {
+    if (warp == C::WORK_WARPS + C::SORT_WARPS) {
         // ================================ DMA warp ================================
         if (lane != 0) return;
         auto store_tile = [&](uint32_t k) {
             const uint32_t s = k & 1u, nt = tile_blocks(k);
-            const uint64_t g0 = r0 + (uint64_t)k * tsz;
+            const uint64_t g0 = r0 + tile_start(k);
             fence_async_smem();
             if (TARGET == TGT_RGBA) {
                 // four pixel rows per block row; a tile may span several block rows
@@ -272,19 +295,21 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
             }
             const uint32_t bytes = tile_blocks(k) * 16u;
             mbar_expect_tx(&bar_full[s], bytes);
-            tma_load_1d(in_s + s * C::TILE, in + r0 + (uint64_t)k * tsz, bytes, &bar_full[s]);
+            tma_load_1d(in_s + s * C::TILE, in + r0 + tile_start(k), bytes, &bar_full[s]);
+            do { if (k < 6) TRACE(k * 6 + 0); } while (0);
         }
         for (uint32_t k = ntiles >= 2 ? ntiles - 2 : 0; k < ntiles; k++) {
             mbar_wait(&bar_done[k & 1u], (k >> 1) & 1u);
             store_tile(k);
         }
         tma_store_wait_all();
+        TRACE(59);
         return;
     }
 
-    if (warp <= C::SORT_WARPS) {
+    if (warp >= C::WORK_WARPS) {
         // ================================ sorter warps ================================
-        const int sw = warp - 1, st = tid - 32;
+        const int sw = warp - C::WORK_WARPS, st = tid - 32 * C::WORK_WARPS;
         uint32_t* mycnt = wcnt + sw * 32;
         for (uint32_t k = 0; k < ntiles; k++) {
             const uint32_t s = k & 1u, u = k >> 1, nt = tile_blocks(k);
@@ -292,27 +317,52 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
             mycnt[lane] = 0;
             __syncwarp();
             mbar_wait(&bar_full[s], u & 1u);
-            // A: classify, rank inside (warp, mode)
+            if (st == 0) do { if (k < 6) TRACE(k * 6 + 1); } while (0);
+            // A: classify, rank inside (warp, mode).  Shared-memory latency is hundreds of cycles while the workers
+            // keep the LSU busy, so every step is a branch-free pass over all of the thread's blocks (PERS loads /
+            // atomics in flight); passes are cut short on the two short start-up tiles (jmax is warp-uniform).
+            const int jmax = (int)((nt + C::SORT_THREADS - 1) / C::SORT_THREADS);
+#ifdef B2BU_TRACE
+#define PH(n) do { if (k == 4 && lane == 0 && (sw == 0 || sw == C::SORT_WARPS - 1)) TRACE(40 + (sw ? 10 : 0) + (n)); } while (0)
+#else
+#define PH(n) do { } while (0)
+#endif
+            PH(0);
             uint32_t mr[C::PERS];
 #pragma unroll
             for (int j = 0; j < C::PERS; j++) {
                 const uint32_t idx = st + j * C::SORT_THREADS;
-                uint32_t m = 31u, rank = 0u;
-                if (idx < nt) {
-                    m = T.mode_lut[tin[idx].x & 127u];
-                    rank = atom_add_shared(&mycnt[m], 1u);
-                }
-                mr[j] = m | (rank << 8);
+                mr[j] = 31u;
+                if (j < jmax) mr[j] = tin[idx < nt ? idx : nt - 1u].x & 127u;
             }
+#pragma unroll
+            for (int j = 0; j < C::PERS; j++) {
+                if (j < jmax) {
+                    const uint32_t lut = T.mode_lut[mr[j]];
+                    mr[j] = (uint32_t)(st + j * C::SORT_THREADS) < nt ? lut : 31u;     // 31 = unused bin
+                }
+            }
+            PH(1);
+            {
+                // rank = old value of the warp's private counter (direct atomics: a MATCH.ANY / ballot + leader
+                // scheme measured 2-3x slower because each step waits for the previous atomic's round trip)
+                uint32_t rk[C::PERS];
+#pragma unroll
+                for (int j = 0; j < C::PERS; j++) if (j < jmax) rk[j] = atomicAdd(&mycnt[mr[j]], 1u);
+#pragma unroll
+                for (int j = 0; j < C::PERS; j++) if (j < jmax) mr[j] |= rk[j] << 8;
+            }
+            PH(2);
             named_bar_sync(1, C::SORT_THREADS);
+            PH(3);
             // B: bin offsets (each bin padded to a multiple of 32, heaviest mode first), item table
             if (sw == 0) {
                 const uint32_t bin = lane < kBins ? (uint32_t)kBinOrder[lane] : 31u;
-                uint32_t c = 0;
-                if (lane < kBins) {
+                uint32_t cw[C::SORT_WARPS], c = 0;
 #pragma unroll
-                    for (int w = 0; w < C::SORT_WARPS; w++) { wbase[w * 32 + bin] = c; c += wcnt[w * 32 + bin]; }
-                }
+                for (int w = 0; w < C::SORT_WARPS; w++) cw[w] = wcnt[w * 32 + bin];
+#pragma unroll
+                for (int w = 0; w < C::SORT_WARPS; w++) { const uint32_t v = lane < kBins ? cw[w] : 0u; cw[w] = c; c += v; }
                 const uint32_t padded = (c + 31u) & ~31u;
                 uint32_t incl = padded;
 #pragma unroll
@@ -320,7 +370,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
                 const uint32_t excl = incl - padded;
                 if (lane < kBins) {
 #pragma unroll
-                    for (int w = 0; w < C::SORT_WARPS; w++) wbase[w * 32 + bin] += excl;
+                    for (int w = 0; w < C::SORT_WARPS; w++) wbase[w * 32 + bin] = cw[w] + excl;
                     for (uint32_t j = 0; j < (padded >> 5); j++) {
                         const uint32_t lanes = c - 32u * j < 32u ? c - 32u * j : 32u;
                         info[s * C::MAXITEMS + (excl >> 5) + j] = (uint16_t)(bin | (lanes << 8));
@@ -328,17 +378,24 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
                 }
                 if (lane == 31) { ctl[s * 4 + 0] = 0; ctl[s * 4 + 1] = incl >> 5; }
             }
+            PH(4);
             named_bar_sync(1, C::SORT_THREADS);
+            PH(5);
             // C: scatter block indices into their bins
             const uint32_t* mybase = wbase + sw * 32;
             uint16_t* ord = order + s * C::MAXORD;
+            {
+                uint32_t bs[C::PERS];
 #pragma unroll
-            for (int j = 0; j < C::PERS; j++) {
-                const uint32_t m = mr[j] & 0xFFu;
-                if (m < (uint32_t)kBins) ord[mybase[m] + (mr[j] >> 8)] = (uint16_t)(st + j * C::SORT_THREADS);
+                for (int j = 0; j < C::PERS; j++) if (j < jmax) bs[j] = mybase[mr[j] & 0xFFu];
+#pragma unroll
+                for (int j = 0; j < C::PERS; j++)
+                    if (j < jmax && (mr[j] & 0xFFu) < (uint32_t)kBins) ord[bs[j] + (mr[j] >> 8)] = (uint16_t)(st + j * C::SORT_THREADS);
             }
+            PH(6);
             named_bar_sync(1, C::SORT_THREADS);
-            if (st == 0) mbar_arrive(&bar_sorted[s]);
+            PH(7);
+            if (st == 0) { mbar_arrive(&bar_sorted[s]); do { if (k < 6) TRACE(k * 6 + 2); } while (0); }
         }
         return;
     }
@@ -350,8 +407,14 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
         unsigned char* tout = out_s + s * C::OUT_SLOT;
         const uint16_t* ord = order + s * C::MAXORD;
         const uint16_t* inf = info + s * C::MAXITEMS;
-        const uint64_t base = r0 + (uint64_t)k * tsz;
+        const uint64_t base = r0 + tile_start(k);
+#ifdef B2BU_TRACE
+        const long long tw0 = clock64();
+#endif
         mbar_wait(&bar_sorted[s], u & 1u);
+#ifdef B2BU_TRACE
+        if (lane == 0) { if (warp == 0) { TRACE_ADD(61, clock64() - tw0); do { if (k < 6) TRACE(k * 6 + 3); } while (0); } if (warp == C::WORK_WARPS - 1) TRACE_ADD(62, clock64() - tw0); }
+#endif
         mbar_wait(&bar_full[s], u & 1u);          // completed long ago: observes the bulk-copied bytes directly
         const uint32_t nitems = ctl[s * 4 + 1];
         for (;;) {
@@ -382,7 +445,9 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
         fence_async_smem();                       // generic-proxy writes -> visible to the bulk store
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_done[s]);
+        if (lane == 0 && warp == 0) do { if (k < 6) TRACE(k * 6 + 4); } while (0);
     }
+    if (lane == 0 && warp == 0) TRACE(63);
 }
 
 template <int TARGET>
@@ -435,5 +500,13 @@ cudaError_t launch_uastc_transcode(int target, const void* d_in, void* d_out, ui
     }
     return cudaGetLastError();
 }
+
+#ifdef B2BU_TRACE
+extern "C" __attribute__((visibility("default"))) int b2bu_debug_trace(unsigned long long* dst, int reset)
+{
+    if (reset) { static unsigned long long z[160][64]; return (int)cudaMemcpyToSymbol(g_trace, z, sizeof z); }
+    return (int)cudaMemcpyFromSymbol(dst, g_trace, sizeof(unsigned long long) * 160 * 64);
+}
+#endif
 
 }  // namespace b2bu
