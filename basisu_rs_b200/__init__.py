@@ -85,6 +85,7 @@ def lib() -> ctypes.CDLL:
     L.b2bu_etc1s_transcode_to_etc1.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, u8p, sz, u8p, sz]
     L.b2bu_etc1s_decode_to_rgba.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, u8p, sz, u8p, sz, u8p, sz]
     L.b2bu_etc1s_transcode_slices.argtypes = [c.c_void_p, c.c_int, c.c_uint32, c.c_uint32, u8p, sz, u64p, u64p, c.c_uint32, u8p, sz]
+    L.b2bu_etc1s_last_timing.argtypes = [c.c_void_p, c.POINTER(c.c_float), c.POINTER(c.c_float), c.POINTER(c.c_float), u64p]
     L.b2bu_read_header.argtypes = [u8p, sz, c.c_void_p]
     L.b2bu_crc16.restype = c.c_uint16
     L.b2bu_crc16.argtypes = [u8p, sz, c.c_uint16]

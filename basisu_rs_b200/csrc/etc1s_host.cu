@@ -156,6 +156,9 @@ struct b2bu_etc1s {
     void* d_scratch = nullptr; size_t scratch_cap = 0;
     void* d_jobs = nullptr; size_t jobs_cap = 0;
     void* d_status = nullptr; size_t status_cap = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // phase boundaries of the last call: H2D | K2 | K3 | D2H
+    float last_ms[3] = {0.f, 0.f, 0.f};
+    uint64_t last_blocks = 0, last_in_bytes = 0, last_out_bytes = 0;
     std::mutex mu;
 };
 
@@ -218,6 +221,9 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
         if (slices[i].len) CK(cudaMemcpyAsync(static_cast<uint8_t*>(h->d_data) + jobs[i].data_ofs, slices[i].data, slices[i].len, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(h->d_jobs, jobs.data(), ns * sizeof(Etc1sSliceJob), cudaMemcpyHostToDevice, s));
 
+    for (int i = 0; i < 4; i++) if (!h->ev[i]) CK(cudaEventCreate(&h->ev[i]));
+    CK(cudaEventRecord(h->ev[0], s));
+
     Etc1sDecodeParams P;
     P.data = static_cast<const uint8_t*>(h->d_data);
     P.jobs = static_cast<const Etc1sSliceJob*>(h->d_jobs);
@@ -232,6 +238,7 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
     const int warps = ns >= (size_t)c->sm_count * 8 ? 4 : 1;
     CK(launch_etc1s_decode(P, warps, s));
     count_launch(1);
+    CK(cudaEventRecord(h->ev[1], s));
 
     const uint32_t* idx = static_cast<const uint32_t*>(h->d_idx);
     if (target == B2BU_ETC1) {
@@ -247,10 +254,14 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
             count_launch(1);
         }
     }
+    CK(cudaEventRecord(h->ev[2], s));
     std::vector<uint32_t> status(ns);
     CK(cudaMemcpyAsync(status.data(), h->d_status, ns * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out, h->d_out, out_total, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(h->ev[3], s));
     CK(cudaStreamSynchronize(s));
+    for (int i = 0; i < 3; i++) cudaEventElapsedTime(&h->last_ms[i], h->ev[i], h->ev[i + 1]);
+    h->last_blocks = blocks_total; h->last_in_bytes = data_total; h->last_out_bytes = out_total;
     for (size_t i = 0; i < ns; i++) if (status[i]) return (int)status[i];          // first failing slice in file order
     return B2BU_OK;
 }
@@ -385,10 +396,22 @@ void b2bu_etc1s_close(b2bu_etc1s* h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
+    for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     cudaFree(h->d_endpoints); cudaFree(h->d_sel_plain); cudaFree(h->d_sel_etc1); cudaFree(h->d_l1);
     for (int t = 0; t < 4; t++) cudaFree(h->d_flat[t]);
     cudaFree(h->d_data); cudaFree(h->d_idx); cudaFree(h->d_out); cudaFree(h->d_scratch); cudaFree(h->d_jobs); cudaFree(h->d_status);
     delete h;
+}
+
+int b2bu_etc1s_last_timing(b2bu_etc1s* h, float* entropy_ms, float* gather_ms, float* d2h_ms, uint64_t* blocks)
+{
+    if (!h) return B2BU_ERR_ARGUMENT;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (entropy_ms) *entropy_ms = h->last_ms[0];
+    if (gather_ms) *gather_ms = h->last_ms[1];
+    if (d2h_ms) *d2h_ms = h->last_ms[2];
+    if (blocks) *blocks = h->last_blocks;
+    return B2BU_OK;
 }
 
 int b2bu_etc1s_transcode_slices(b2bu_etc1s* h, int target, uint32_t nbx, uint32_t nby, const uint8_t* data, size_t data_len,

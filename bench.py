@@ -175,6 +175,125 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+
+def mip_chain_blocks(size=8192):
+    """BASELINE configs[2]: 8192^2 with the full mip chain, level k has ceil(max(1, size >> k) / 4)^2 blocks."""
+    out, k = [], 0
+    while True:
+        d = max(1, size >> k)
+        nb = (d + 3) // 4
+        out.append(nb)
+        if d == 1:
+            break
+        k += 1
+    return out
+
+
+def bench_c3_bc7_mips(L, torch, payload, steps, status, sh):
+    """configs[2]: UASTC -> BC7 over an 8192^2 texture with its full mip chain (14 slices, one launch each)."""
+    dims = mip_chain_blocks()
+    total = sum(d * d for d in dims)
+    blocks = make_payload(payload, total, seed=7)
+    d_in = torch.from_numpy(blocks.reshape(-1)).cuda()
+    d_out = [torch.empty(total * 16, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    offs = np.cumsum([0] + [d * d for d in dims])
+
+    def chain(i):
+        for lv, d in enumerate(dims):
+            n = d * d
+            st = L.b2bu_uastc_transcode_dev(2, d_in.data_ptr() + int(offs[lv]) * 16, n * 16, d, d_out[i & 1].data_ptr() + int(offs[lv]) * 16, n * 16,
+                                            status.data_ptr(), sh)
+            assert st == 0
+    for i in range(3):
+        chain(i)
+    torch.cuda.synchronize()
+    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        chain(i)
+    c.record()
+    torch.cuda.synchronize()
+    us = a.elapsed_time(c) / steps * 1e3
+    orc = load_oracle()
+    ns = min(total, 1 << 18)
+    want = np.zeros(ns * 16, dtype=np.uint8)
+    orc.orc_uastc_transcode_slice(2, blocks.ctypes.data, ns * 16, 1, want.ctypes.data, os.cpu_count() or 1, None)
+    # level 0 holds the first blocks of the payload; the tail levels are checked whole
+    ok = bool((d_out[(steps - 1) & 1][: ns * 16].cpu().numpy() == want).all())
+    tail0 = int(offs[3])
+    want_t = np.zeros((total - tail0) * 16, dtype=np.uint8)
+    orc.orc_uastc_transcode_slice(2, blocks[tail0:].ctypes.data, (total - tail0) * 16, 1, want_t.ctypes.data, os.cpu_count() or 1, None)
+    ok = ok and bool((d_out[(steps - 1) & 1][tail0 * 16: total * 16].cpu().numpy() == want_t).all())
+    return {"workload": "UASTC->BC7, 8192x8192 + full mip chain (%d levels, %d blocks), one launch per level" % (len(dims), total),
+            "us_per_chain": us, "gtexel_s": total * 16 / us / 1e3, "algo_gb_s": total * 32 / us / 1e3, "launches_per_chain": len(dims),
+            "parity_vs_oracle": ok}
+
+
+def bench_c4_etc1s(L, b, nb=1024, slices=64, n_cb=4096, reps=2):
+    """configs[3]: ETC1S -> ETC1 / RGBA, warp-per-slice entropy decode (K2) + codebook gather (K3), nb x nb blocks x `slices` slices.
+    One slice is encoded by the test encoder on a procedural index map and replicated (the decoder keeps no state across slices)."""
+    import etc1s_common as ec
+    from etc1s_synth import encode, make_codebooks, make_indices
+    orc = ec.bind(load_oracle())
+    ep_cb, sel_cb = make_codebooks(n_cb, n_cb, seed=3)
+    ei, si = make_indices(nb, nb, 1, n_cb, n_cb, seed=4)
+    enc = encode(orc, ep_cb, sel_cb, ei, si, nb, nb, 64, False, False)
+    one = ec.slice_bytes(enc, 0)
+    pad = (-len(one)) % 16
+    data = (one + b"\0" * pad) * slices
+    ofs = (ctypes.c_uint64 * slices)(*[i * (len(one) + pad) for i in range(slices)])
+    lens = (ctypes.c_uint64 * slices)(*[len(one)] * slices)
+    dec = b.Etc1sDecoder(n_cb, n_cb, enc["endpoints"], enc["selectors"], enc["tables"])
+    nblk = nb * nb * slices
+    res = {"workload": "ETC1S %dx%d blocks x %d slices (one encoded slice replicated), %d-entry codebooks" % (nb, nb, slices, n_cb),
+           "compressed_bytes_per_slice": len(one), "bits_per_block": 8.0 * len(one) / (nb * nb)}
+    buf = ctypes.create_string_buffer(data, len(data))
+    import torch
+    for tname, t, ob in (("etc1", 3, 8), ("rgba", 0, 64)):
+        if t == 0 and nblk * 64 > (8 << 30):
+            continue
+        out = torch.empty(nblk * ob, dtype=torch.uint8).pin_memory()
+        best = None
+        for r in range(reps + 1):
+            t0 = time.perf_counter()
+            st = L.b2bu_etc1s_transcode_slices(dec._h, t, nb, nb, buf, len(data), ofs, lens, slices, out.data_ptr(), nblk * ob)
+            wall = time.perf_counter() - t0
+            assert st == 0, st
+            k2, k3, d2h, nbk = ctypes.c_float(), ctypes.c_float(), ctypes.c_float(), ctypes.c_uint64()
+            L.b2bu_etc1s_last_timing(dec._h, ctypes.byref(k2), ctypes.byref(k3), ctypes.byref(d2h), ctypes.byref(nbk))
+            if r and (best is None or k2.value + k3.value < best[0] + best[1]):
+                best = (k2.value, k3.value, d2h.value, wall)
+        k2, k3, d2h, wall = best
+        # parity on slice 0 and the last slice against the oracle's serial decode
+        h = ctypes.c_void_p()
+        assert orc.orc_etc1s_open(n_cb, n_cb, enc["endpoints"], len(enc["endpoints"]), enc["selectors"], len(enc["selectors"]), enc["tables"],
+                                  len(enc["tables"]), 0, ctypes.byref(h)) == 0
+        if t == 3:
+            e, want = ec.oracle_etc1(orc, h, nb, nb, one)
+        else:
+            e, want = ec.oracle_rgba(orc, h, nb, nb, one)
+        orc.orc_etc1s_close(h)
+        per = nb * nb * ob
+        got = out.numpy()
+        ok = e == 0 and got[:per].tobytes() == want and got[(slices - 1) * per:].tobytes() == want
+        res[tname] = {"entropy_ms": k2, "gather_ms": k3, "d2h_ms": d2h, "wall_ms": wall * 1e3,
+                      "device_gtexel_s": nblk * 16 / ((k2 + k3) * 1e-3) / 1e9, "e2e_gtexel_s": nblk * 16 / wall / 1e9,
+                      "gather_algo_gb_s": nblk * (4 + ob) / (k3 * 1e-3) / 1e9, "entropy_mblocks_s_per_slice": nb * nb / (k2 * 1e-3) / 1e6,
+                      "parity_vs_oracle": bool(ok)}
+        del out
+    # CPU port on the same slice, one thread per slice
+    t0 = time.perf_counter()
+    h = ctypes.c_void_p()
+    orc.orc_etc1s_open(n_cb, n_cb, enc["endpoints"], len(enc["endpoints"]), enc["selectors"], len(enc["selectors"]), enc["tables"], len(enc["tables"]), 0,
+                       ctypes.byref(h))
+    ec.oracle_etc1(orc, h, nb, nb, one)
+    orc.orc_etc1s_close(h)
+    dt = time.perf_counter() - t0
+    res["cpu_port_one_thread_gtexel_s"] = nb * nb * 16 / dt / 1e9
+    dec.close()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -190,6 +309,10 @@ def main():
     ap.add_argument("--cpu-sample-blocks", type=int, default=1 << 20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--all-targets", action="store_true", help="also report the other targets / payloads in 'extra'")
+    ap.add_argument("--configs", default="c3,c4", help="extra BASELINE configs measured on rank 0 and reported under 'configs' (c3 = BC7 mip chain, "
+                    "c4 = ETC1S slices); '' to skip")
+    ap.add_argument("--c4-blocks", type=int, default=1024, help="ETC1S slice edge in blocks (1024 = 4096x4096 texels)")
+    ap.add_argument("--c4-slices", type=int, default=64)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -326,6 +449,16 @@ def main():
                 extra[f"{tn}/{pk}"] = {"us_per_launch": us, "gtexel_s": n * 16 / us / 1e3, "algo_gb_s": n * ALGO_BYTES[tt] / us / 1e3}
                 del di, do
 
+    cfgs = {}
+    if rank == 0 and args.configs:
+        want_cfg = set(args.configs.split(","))
+        if "c3" in want_cfg:
+            cfgs["c3_bc7_mip_chain"] = bench_c3_bc7_mips(L, torch, args.payload, 50, status, sh)
+        if "c4" in want_cfg:
+            cfgs["c4_etc1s"] = bench_c4_etc1s(L, b, args.c4_blocks, args.c4_slices)
+    if world > 1:
+        dist.barrier()
+
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         achieved = n * ALGO_BYTES[target] / (ms_per_step * 1e-3) / 1e9
@@ -352,6 +485,8 @@ def main():
         }
         if extra:
             line["extra"] = extra
+        if cfgs:
+            line["configs"] = cfgs
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -127,6 +127,11 @@ int b2bu_etc1s_transcode_slices(b2bu_etc1s* h, int target, uint32_t nbx, uint32_
                                 const uint64_t* slice_ofs, const uint64_t* slice_len, uint32_t num_slices,
                                 uint8_t* out, size_t out_bytes);
 
+/* Device-side duration of the phases of the last call on this handle (CUDA events on the call's stream):
+ * K2 entropy decode (all slices), K3 codebook gather, and the D2H copy of the result.  The phases are
+ * reported separately because K2 is a latency-bound serial chain per slice while K3 is HBM-bound. */
+int b2bu_etc1s_last_timing(b2bu_etc1s* h, float* entropy_ms, float* gather_ms, float* d2h_ms, uint64_t* blocks);
+
 /* ---- file level: src/basis.rs:8-260, src/lib.rs:63-79 ---------------------------------------- */
 typedef struct b2bu_header {       /* basis.rs:419-454 (all 26 fields, widened to u32) */
     uint32_t sig, ver, header_size, header_crc16, data_size, data_crc16, total_slices, total_images, tex_format,

@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick device-resident timing of all targets (kat-shuffled); usage: tools/quick_bench.sh [lib.so]
 [ -n "$1" ] && export B2BU_LIBRARY=$PWD/basisu_rs_b200/$1
-python bench.py --all-targets --no-cpu-baseline --steps 50 --e2e-steps 5 > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err || tail -5 gpurun_out/bench_q.err
+python bench.py --all-targets --no-cpu-baseline --configs none --steps 50 --e2e-steps 5 > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err || tail -5 gpurun_out/bench_q.err
 python - <<'PY'
 import json
 d = json.load(open("gpurun_out/bench_q.json"))
