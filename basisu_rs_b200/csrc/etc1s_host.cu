@@ -38,6 +38,13 @@ struct BitCursor {
 struct HuffModel {
     std::vector<uint32_t> flat;     // 1 << max_len entries of symbol << 5 | code size (0 = no code), as huffman.rs:151-170 fills them
     unsigned max_len = 0;
+    // canonical form for the kernel's long-code path (valid prefix codes only, else canon_ok = false and the kernel reads `flat`):
+    // a 16-bit MSB-first window v has a code of length l iff v < upper[l-1] and v >= upper[l-2]; its symbol is
+    // syms[base[l-1] + (v >> (16 - l))]
+    bool canon_ok = false;
+    uint32_t upper[16] = {0};
+    int32_t base[16] = {0};
+    std::vector<uint16_t> syms;     // symbols sorted by (code length, symbol)
 };
 
 static uint32_t bit_reverse32(uint32_t x)
@@ -78,6 +85,24 @@ static int huff_from_sizes(const std::vector<uint8_t>& sizes, HuffModel& m)
         next[size]++;
     }
     for (unsigned b = 0; b <= 16; b++) if (next[b] > 65536u) return B2BU_ERR_HUFFMAN;   // "codes don't fit into 16 bits"
+    // canonical description (only meaningful for a prefix-free set: Kraft sum <= 1)
+    uint64_t kraft = 0;
+    for (unsigned b = 1; b <= 16; b++) kraft += (uint64_t)count[b] << (16 - b);
+    m.canon_ok = kraft <= 65536u && sizes.size() <= 65536u;
+    if (m.canon_ok) {
+        uint32_t first = 0, ofs = 0, offset[17] = {0};
+        for (unsigned b = 1; b <= 16; b++) {
+            first = (first + count[b - 1]) << 1;
+            offset[b] = ofs;
+            m.upper[b - 1] = (first + count[b]) << (16 - b);
+            m.base[b - 1] = (int32_t)ofs - (int32_t)first;
+            ofs += count[b];
+        }
+        m.syms.assign(ofs, 0);
+        uint32_t fill[17];
+        for (unsigned b = 0; b <= 16; b++) fill[b] = offset[b];
+        for (size_t sym = 0; sym < sizes.size(); sym++) if (sizes[sym]) m.syms[fill[sizes[sym]]++] = (uint16_t)sym;
+    }
     return B2BU_OK;
 }
 
@@ -149,6 +174,10 @@ struct b2bu_etc1s {
     uint32_t* d_sel_etc1 = nullptr;      // ETC1 bit planes               (etc.rs:363-393)
     uint32_t* d_l1 = nullptr;            // 4 x 1024
     uint32_t* d_flat[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t* d_canon = nullptr;         // 4 x {16 upper, 16 base}
+    uint16_t* d_syms = nullptr;          // the four sorted symbol arrays back to back
+    uint32_t sym_ofs[5] = {0, 0, 0, 0, 0};
+    uint32_t canon_ok = 0;               // bit t: table t has a canonical description
     // per-call scratch (grow only)
     void* d_data = nullptr; size_t data_cap = 0;
     void* d_idx = nullptr; size_t idx_cap = 0;
@@ -202,13 +231,15 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
     if (ns == 0) return B2BU_OK;
     std::vector<Etc1sSliceJob> jobs(ns);
     uint64_t data_total = 0, blocks_total = 0, scratch_total = 0;
+    uint32_t max_nbx = 0;
     for (size_t i = 0; i < ns; i++) {
         jobs[i].data_ofs = data_total; jobs[i].data_len = slices[i].len;
         jobs[i].out_ofs = blocks_total; jobs[i].scratch_ofs = scratch_total;
         jobs[i].nbx = slices[i].nbx; jobs[i].nby = slices[i].nby;
         data_total += (slices[i].len + 15) & ~15ull;
         blocks_total += (uint64_t)slices[i].nbx * slices[i].nby;
-        scratch_total += ((slices[i].nbx + 15ull) & ~15ull) + (h->hist_size > 64 ? ((2ull * h->hist_size + 15) & ~15ull) : 0);
+        scratch_total += etc1s_row_state_bytes(slices[i].nbx) + (h->hist_size > 64 ? ((2ull * h->hist_size + 15) & ~15ull) : 0);
+        max_nbx = std::max(max_nbx, slices[i].nbx);
     }
     if ((st = ensure(&h->d_data, &h->data_cap, data_total + 16))) return st;
     if ((st = ensure(&h->d_idx, &h->idx_cap, blocks_total * 4 + 16))) return st;
@@ -231,12 +262,14 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
     P.out_idx = static_cast<uint32_t*>(h->d_idx);
     P.scratch = static_cast<uint8_t*>(h->d_scratch);
     P.l1 = h->d_l1;
-    for (int t = 0; t < 4; t++) { P.flat[t] = h->d_flat[t]; P.max_len[t] = h->max_len[t]; }
+    for (int t = 0; t < 4; t++) { P.flat[t] = h->d_flat[t]; P.max_len[t] = h->max_len[t]; P.sym_ofs[t] = h->sym_ofs[t]; }
+    P.sym_ofs[4] = h->sym_ofs[4]; P.canon = h->d_canon; P.syms = h->d_syms; P.canon_ok = h->canon_ok;
     P.num_endpoints = h->num_endpoints; P.num_selectors = h->num_selectors; P.hist_size = h->hist_size; P.is_video = h->is_video ? 1u : 0u;
     P.status = static_cast<uint32_t*>(h->d_status);
-    // one warp per slice; spread slices over SMs first, pack warps only when there are many slices
-    const int warps = ns >= (size_t)c->sm_count * 8 ? 4 : 1;
-    CK(launch_etc1s_decode(P, warps, s));
+    // one warp per slice; spread slices over SMs first, pack warps (which share the tables in shared memory) when there are many slices:
+    // a lone warp issues one dependent instruction every ~6 cycles, 16 warps per SM keep the issue slots busy
+    const int warps = ns >= (size_t)c->sm_count * 16 ? 16 : ns >= (size_t)c->sm_count * 4 ? 4 : 1;
+    CK(launch_etc1s_decode(P, warps, max_nbx, s));
     count_launch(1);
     CK(cudaEventRecord(h->ev[1], s));
 
@@ -339,6 +372,22 @@ static int etc1s_open_impl(uint32_t endpoint_count, uint32_t selector_count, con
     if ((st = upload(&h->d_endpoints, endpoints)) || (st = upload(&h->d_sel_plain, sel_plain)) || (st = upload(&h->d_sel_etc1, sel_etc1)) ||
         (st = upload(&h->d_l1, l1))) return st;
     for (int t = 0; t < 4; t++) if ((st = upload(&h->d_flat[t], models[t].flat))) return st;
+    {
+        std::vector<uint32_t> canon(4 * 32, 0);
+        std::vector<uint16_t> syms;
+        for (int t = 0; t < 4; t++) {
+            h->sym_ofs[t] = (uint32_t)syms.size();
+            if (!models[t].canon_ok) continue;
+            h->canon_ok |= 1u << t;
+            for (int l = 0; l < 16; l++) { canon[t * 32 + l] = models[t].upper[l]; canon[t * 32 + 16 + l] = (uint32_t)models[t].base[l]; }
+            syms.insert(syms.end(), models[t].syms.begin(), models[t].syms.end());
+        }
+        h->sym_ofs[4] = (uint32_t)syms.size();
+        if ((st = upload(&h->d_canon, canon))) return st;
+        syms.resize((syms.size() + 1) & ~size_t(1), 0);
+        CK(cudaMalloc(&h->d_syms, std::max<size_t>(syms.size(), 2) * 2));
+        if (!syms.empty()) CK(cudaMemcpy(h->d_syms, syms.data(), syms.size() * 2, cudaMemcpyHostToDevice));
+    }
     *out = h.release();
     return B2BU_OK;
 }
@@ -399,6 +448,7 @@ void b2bu_etc1s_close(b2bu_etc1s* h)
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     cudaFree(h->d_endpoints); cudaFree(h->d_sel_plain); cudaFree(h->d_sel_etc1); cudaFree(h->d_l1);
     for (int t = 0; t < 4; t++) cudaFree(h->d_flat[t]);
+    cudaFree(h->d_canon); cudaFree(h->d_syms);
     cudaFree(h->d_data); cudaFree(h->d_idx); cudaFree(h->d_out); cudaFree(h->d_scratch); cudaFree(h->d_jobs); cudaFree(h->d_status);
     delete h;
 }

@@ -22,50 +22,80 @@ constexpr int kL1Bits = 10;
 constexpr int kL1Size = 1 << kL1Bits;
 constexpr uint32_t kLong = 0xFFFFFFFFu;          // first-level entry: code longer than kL1Bits
 constexpr int kRound = 32;                        // blocks decoded between two cooperative phases
-constexpr int kWinWords = 256;                    // compressed-byte window per warp (1 KiB)
+constexpr int kHalfBytes = 1024;                  // the compressed-byte ring is refilled in 1 KiB pieces
+constexpr int kRingHalves = 4;                    // 4 KiB ring per warp: the piece being read, the next, one in flight
+constexpr int kRingWords = kRingHalves * kHalfBytes / 4;
+// A round of 32 blocks consumes well under one piece: per block at most one predictor symbol (16 bits) with
+// a 4-bit-chunk VLC (40), a delta (16), a selector symbol (16), a run symbol (16) and a 7-bit-chunk VLC (40).
+static_assert(kRound * 144 / 8 <= kHalfBytes, "ring piece too small for one round");
 
 struct WarpShared {
-    uint32_t win[kWinWords];
-    uint32_t stage[kRound];
-    uint32_t up[kRound + 1];                      // endpoint indices of the previous row, x0-1 .. x0+31
+    uint32_t ring[kRingWords];
     uint16_t hist[64];                            // selector history when it fits (it always does for real files)
 };
 
-struct BitState { uint64_t buf; int avail; uint32_t nextw; };
+struct BitState { uint64_t buf; int avail; uint32_t nextw; };                     // nextw: absolute word index in the slice
 
-__device__ __forceinline__ void bits_ensure32(BitState& s, const uint32_t* win)
+__device__ __forceinline__ void bits_ensure32(BitState& s, const uint32_t* ring)
 {
     if (s.avail < 32) {
-        const uint32_t w = s.nextw < (uint32_t)kWinWords ? win[s.nextw] : 0u;
-        s.buf |= (uint64_t)w << s.avail;
+        s.buf |= (uint64_t)ring[s.nextw & (kRingWords - 1)] << s.avail;
         s.avail += 32;
         s.nextw++;
     }
 }
-__device__ __forceinline__ void bits_skip(BitState& s, uint32_t n, uint64_t& consumed) { s.buf >>= n; s.avail -= (int)n; consumed += n; }
+__device__ __forceinline__ void bits_skip(BitState& s, uint32_t n) { s.buf >>= n; s.avail -= (int)n; }
+
+// One Huffman model as the warp sees it: 10-bit first-level table in shared memory for the short codes; longer
+// codes are resolved by a warp-parallel canonical decode (lane l tests code length l+1 against its `upper`
+// bound, a ballot picks the length, a shuffle fetches the symbol index) so that no code needs a global-memory
+// round trip on the serial chain.  `flat` is only read for tables that are not valid prefix codes.
+struct HuffView {
+    const uint32_t* l1;            // shared
+    const uint16_t* syms;          // shared (or global when the symbol arrays do not fit)
+    const uint32_t* flat;          // global
+    uint32_t upper;                // this lane's length bound
+    int32_t base;
+    uint32_t max_len;
+    bool canon;
+};
 
 // huffman.rs:186-198 decode_symbol.  Returns the symbol or 0xFFFFFFFF when no code matches.
-__device__ __forceinline__ uint32_t huff_decode(BitState& s, const uint32_t* win, const uint32_t* l1, const uint32_t* __restrict__ flat,
-                                                uint32_t max_len, uint64_t& consumed)
+__device__ __forceinline__ uint32_t huff_decode(BitState& s, const uint32_t* ring, const HuffView& h, int lane)
 {
-    bits_ensure32(s, win);
-    uint32_t e = l1[(uint32_t)s.buf & (kL1Size - 1)];
-    if (e == kLong) e = __ldg(flat + ((uint32_t)s.buf & ((1u << max_len) - 1u)));
-    const uint32_t len = e & 31u;
+    bits_ensure32(s, ring);
+    const uint32_t e = h.l1[(uint32_t)s.buf & (kL1Size - 1)];
+    if (e != kLong) {
+        const uint32_t len = e & 31u;
+        if (len == 0u) return 0xFFFFFFFFu;
+        bits_skip(s, len);
+        return e >> 5;
+    }
+    if (h.canon) {
+        const uint32_t v = __brev((uint32_t)s.buf) >> 16;                          // next 16 stream bits, first bit most significant
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, v < h.upper) & 0xFFFFu;
+        if (bal == 0u) return 0xFFFFFFFFu;
+        const uint32_t len = (uint32_t)__ffs((int)bal);                            // 1..16
+        const uint32_t idx = __shfl_sync(0xFFFFFFFFu, (uint32_t)(h.base + (int32_t)(v >> (15 - (lane & 15)))), (int)len - 1);
+        bits_skip(s, len);
+        return h.syms[idx];
+    }
+    const uint32_t f = __ldg(h.flat + ((uint32_t)s.buf & ((1u << h.max_len) - 1u)));
+    const uint32_t len = f & 31u;
     if (len == 0u) return 0xFFFFFFFFu;
-    bits_skip(s, len, consumed);
-    return e >> 5;
+    bits_skip(s, len);
+    return f >> 5;
 }
 
 // mod.rs:585-608 decode_vlc.  Returns false when the reference would panic (ofs >= 32).
-__device__ __forceinline__ bool vlc_decode(BitState& s, const uint32_t* win, uint32_t chunk_bits, uint32_t& v, uint64_t& consumed)
+__device__ __forceinline__ bool vlc_decode(BitState& s, const uint32_t* ring, uint32_t chunk_bits, uint32_t& v)
 {
     v = 0;
     uint32_t ofs = 0;
     for (;;) {
-        bits_ensure32(s, win);
+        bits_ensure32(s, ring);
         const uint32_t c = (uint32_t)s.buf & ((2u << chunk_bits) - 1u);
-        bits_skip(s, chunk_bits + 1, consumed);
+        bits_skip(s, chunk_bits + 1);
         v |= (c & ((1u << chunk_bits) - 1u)) << ofs;
         ofs += chunk_bits;
         if ((c >> chunk_bits) == 0u) return true;
@@ -73,60 +103,101 @@ __device__ __forceinline__ bool vlc_decode(BitState& s, const uint32_t* win, uin
     }
 }
 
-__global__ void __launch_bounds__(128) etc1s_entropy_decode_kernel(Etc1sDecodeParams P)
+// One 1 KiB piece of the slice's bytes -> two uint4 per lane (zeros past the end: bitreader.rs:44,55).
+__device__ __forceinline__ void piece_load(const uint8_t* __restrict__ data, uint64_t data_len, uint32_t piece, int lane, uint4 (&r)[2])
+{
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint64_t o = (uint64_t)piece * kHalfBytes + 16u * (uint32_t)(lane + 32 * k);
+        if (o + 16 <= data_len) r[k] = __ldg(reinterpret_cast<const uint4*>(data + o));        // slices start 16-byte aligned
+        else {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            for (int b = 0; b < 16; b++) if (o + b < data_len) w[b >> 2] |= (uint32_t)data[o + b] << (8 * (b & 3));
+            r[k] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+__device__ __forceinline__ void piece_store(uint32_t* ring, uint32_t piece, int lane, const uint4 (&r)[2])
+{
+    uint4* dst = reinterpret_cast<uint4*>(ring + (piece % kRingHalves) * (kHalfBytes / 4));
+    dst[lane] = r[0];
+    dst[lane + 32] = r[1];
+}
+
+// rows_in_smem: the per-slice row state (endpoint indices and predictor bits of the previous row) lives in shared
+// memory when the slice is at most `row_cap` blocks wide, else in the global scratch area (very wide slices).
+__global__ void __launch_bounds__(512) etc1s_entropy_decode_kernel(Etc1sDecodeParams P, uint32_t row_cap, uint32_t sym_smem_bytes)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* l1s = reinterpret_cast<uint32_t*>(smem_raw);                      // 4 tables x 1024 entries
-    WarpShared* wsh_all = reinterpret_cast<WarpShared*>(smem_raw + 4 * kL1Size * sizeof(uint32_t));
+    const int nwarps = blockDim.x >> 5;
+    uint16_t* syms_s = reinterpret_cast<uint16_t*>(smem_raw + 4 * kL1Size * sizeof(uint32_t));   // sorted symbols (when they fit)
+    WarpShared* wsh_all = reinterpret_cast<WarpShared*>(smem_raw + 4 * kL1Size * sizeof(uint32_t) + sym_smem_bytes);
+    uint16_t* rows_all = reinterpret_cast<uint16_t*>(wsh_all + nwarps);           // per warp: row_cap endpoint indices + row_cap/2 pred bytes
     for (int i = threadIdx.x; i < 4 * kL1Size; i += blockDim.x) l1s[i] = P.l1[i];
+    if (sym_smem_bytes) for (uint32_t i = threadIdx.x; i < (P.sym_ofs[4] + 1u) / 2u; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(syms_s)[i] = reinterpret_cast<const uint32_t*>(P.syms)[i];
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t slice = blockIdx.x * (blockDim.x >> 5) + warp;
+    const uint32_t slice = blockIdx.x * nwarps + warp;
     if (slice >= P.num_slices) return;
     WarpShared& W = wsh_all[warp];
     const Etc1sSliceJob job = P.jobs[slice];
     const uint8_t* __restrict__ data = P.data + job.data_ofs;
     uint32_t* __restrict__ out = P.out_idx + job.out_ofs;
-    uint8_t* predrow = P.scratch + job.scratch_ofs;                               // nbx bytes
-    uint16_t* hist = P.hist_size <= 64u ? W.hist : reinterpret_cast<uint16_t*>(P.scratch + job.scratch_ofs + ((job.nbx + 15u) & ~15u));
     const uint32_t nbx = job.nbx, nby = job.nby;
+    const bool rows_in_smem = nbx <= row_cap;
+    // previous row: endpoint index per block (u16) and the predictor bits of every 2x2 group's lower half (u8 per 2 blocks)
+    uint16_t* rowep = rows_in_smem ? rows_all + (size_t)warp * (row_cap + row_cap / 2 + 8)
+                                   : reinterpret_cast<uint16_t*>(P.scratch + job.scratch_ofs);
+    uint8_t* predrow = reinterpret_cast<uint8_t*>(rowep + (rows_in_smem ? row_cap : ((nbx + 7u) & ~7u)));
+    uint16_t* hist = P.hist_size <= 64u ? W.hist : reinterpret_cast<uint16_t*>(P.scratch + job.scratch_ofs + etc1s_row_state_bytes(nbx));
     const uint32_t num_endpoints = P.num_endpoints, num_selectors = P.num_selectors, hist_size = P.hist_size;
     const uint32_t rle_sym = (hist_size + num_selectors) & 0xFFFFu;               // mod.rs:220-222 (u16 arithmetic)
 
+    HuffView hv[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        hv[t].l1 = l1s + t * kL1Size;
+        hv[t].syms = (sym_smem_bytes ? syms_s : P.syms) + P.sym_ofs[t];
+        hv[t].flat = P.flat[t];
+        hv[t].upper = P.canon[t * 32 + (lane & 15)];
+        hv[t].base = (int32_t)P.canon[t * 32 + 16 + (lane & 15)];
+        hv[t].max_len = P.max_len[t];
+        hv[t].canon = (P.canon_ok >> t) & 1u;
+    }
     for (uint32_t i = lane; i < hist_size; i += 32) hist[i] = 0;                   // mod.rs:616-621
+    // prime the ring with the first three pieces
+    uint32_t loaded = 0;                          // pieces [0, loaded) are (or were) in the ring
+    for (; loaded < 3; loaded++) { uint4 r[2]; piece_load(data, job.data_len, loaded, lane, r); piece_store(W.ring, loaded, lane, r); }
     __syncwarp();
 
-    uint64_t consumed = 0;                        // bits consumed so far
+    BitState bs;
+    bs.buf = ((uint64_t)W.ring[1] << 32) | W.ring[0];
+    bs.avail = 64;
+    bs.nextw = 2;
     uint32_t rover = hist_size / 2, sel_rle = 0, pred_rep = 0, prev_sym = 0, cur = 0, prev_ep = 0;
-    uint32_t err = 0;
+    uint32_t err = 0, carry_up = 0;           // carry_up: previous row's endpoint index of block x0-1 (its slot is overwritten by then)
 
     for (uint32_t y = 0; y < nby && !err; y++) {
         for (uint32_t x0 = 0; x0 < nbx && !err; x0 += kRound) {
             const uint32_t nb = nbx - x0 < (uint32_t)kRound ? nbx - x0 : (uint32_t)kRound;
-            // ---- cooperative: refill the byte window at the current position, fetch the row above ----
-            const uint64_t wbyte = (consumed >> 3) & ~3ull;
-#pragma unroll
-            for (int k = 0; k < kWinWords / 32; k++) {
-                const uint64_t o = wbyte + 4ull * (uint32_t)(lane + 32 * k);
-                uint32_t w = 0;
-                if (o + 4 <= job.data_len) w = (uint32_t)data[o] | ((uint32_t)data[o + 1] << 8) | ((uint32_t)data[o + 2] << 16) | ((uint32_t)data[o + 3] << 24);
-                else for (int b = 0; b < 4; b++) if (o + b < job.data_len) w |= (uint32_t)data[o + b] << (8 * b);   // bitreader.rs:44,55: zeros past the end
-                W.win[lane + 32 * k] = w;
-            }
+            // ---- cooperative: start fetching the next ring piece if the reader is about to need it ----
+            // reader position in pieces; pieces up to pos+2 must be resident before the next round starts
+            const uint32_t pos = (bs.nextw * 4u) / kHalfBytes;
+            const bool fetch = loaded < pos + 3u;                                 // warp-uniform
+            uint4 pre[2];
+            if (fetch) piece_load(data, job.data_len, loaded, lane, pre);
+            // row above (x0-1 .. x0+31) into registers: lane l holds block x0 + l - 1, lane 0 of the next round's view via shfl
+            uint32_t up_mine = carry_up, up_last = 0;
             if (y > 0) {
-                const uint32_t* above = out + (uint64_t)(y - 1) * nbx;
-                if (x0 + lane >= 1 && x0 + lane - 1 < nbx) W.up[lane] = __ldcg(above + x0 + lane - 1) & 0xFFFFu;
-                if (lane == 0 && x0 + 31 < nbx) W.up[32] = __ldcg(above + x0 + 31) & 0xFFFFu;
+                if (lane >= 1 && x0 + lane - 1 < nbx) up_mine = rowep[x0 + lane - 1];
+                if (x0 + 31 < nbx) up_last = rowep[x0 + 31];
             }
-            __syncwarp();
-            BitState bs;
-            {
-                const uint32_t rel = (uint32_t)(consumed - wbyte * 8);            // 0..31
-                bs.buf = (((uint64_t)W.win[1] << 32) | W.win[0]) >> rel;
-                bs.avail = 64 - (int)rel;
-                bs.nextw = 2;
-            }
+            carry_up = up_last;
+            __syncwarp();                          // everyone has read the old row before it is overwritten below
+            uint32_t mine = 0;
             // ---- serial chain, executed redundantly by every lane (mod.rs:245-455) ----
             for (uint32_t b = 0; b < nb; b++) {
                 const uint32_t x = x0 + b;
@@ -134,28 +205,31 @@ __global__ void __launch_bounds__(128) etc1s_entropy_decode_kernel(Etc1sDecodePa
                     if ((y & 1u) == 0u) {
                         if (pred_rep != 0u) { pred_rep--; cur = prev_sym; }
                         else {
-                            const uint32_t s = huff_decode(bs, W.win, l1s + 0 * kL1Size, P.flat[0], P.max_len[0], consumed);
+                            const uint32_t s = huff_decode(bs, W.ring, hv[0], lane);
                             if (s == 0xFFFFFFFFu) { err = ETC1S_ERR_HUFFMAN; break; }
                             if (s == 256u) {
                                 uint32_t v;
-                                if (!vlc_decode(bs, W.win, 4, v, consumed)) { err = ETC1S_ERR_VLC; break; }
+                                if (!vlc_decode(bs, W.ring, 4, v)) { err = ETC1S_ERR_VLC; break; }
                                 pred_rep = v + 3u - 1u;
                                 cur = prev_sym;
                             } else { cur = s & 0xFFu; prev_sym = cur; }
                         }
-                        predrow[x] = (uint8_t)(cur >> 4);
-                    } else cur = predrow[x];
+                        if (lane == 0) predrow[x >> 1] = (uint8_t)(cur >> 4);
+                    } else cur = predrow[x >> 1];
                 }
                 const uint32_t pred = cur & 3u;
                 cur >>= 2;
                 uint32_t ep;
                 if (pred == 0u) { if (x == 0u) { err = ETC1S_ERR_PREDICTION; break; } ep = prev_ep; }
-                else if (pred == 1u) { if (y == 0u) { err = ETC1S_ERR_PREDICTION; break; } ep = W.up[b + 1]; }
+                else if (pred == 1u) {
+                    if (y == 0u) { err = ETC1S_ERR_PREDICTION; break; }
+                    ep = b == 31u ? up_last : __shfl_sync(0xFFFFFFFFu, up_mine, b + 1);
+                }
                 else if (pred == 2u) {
                     if (P.is_video) ep = 0u;                                      // quirk C-5: previous-frame state is always zero
-                    else { if (x == 0u || y == 0u) { err = ETC1S_ERR_PREDICTION; break; } ep = W.up[b]; }
+                    else { if (x == 0u || y == 0u) { err = ETC1S_ERR_PREDICTION; break; } ep = __shfl_sync(0xFFFFFFFFu, up_mine, b); }
                 } else {
-                    const uint32_t d = huff_decode(bs, W.win, l1s + 1 * kL1Size, P.flat[1], P.max_len[1], consumed);
+                    const uint32_t d = huff_decode(bs, W.ring, hv[1], lane);
                     if (d == 0xFFFFFFFFu) { err = ETC1S_ERR_HUFFMAN; break; }
                     ep = (d + prev_ep) & 0xFFFFu;
                     if (ep >= num_endpoints) ep = (ep - num_endpoints) & 0xFFFFu;
@@ -166,15 +240,15 @@ __global__ void __launch_bounds__(128) etc1s_entropy_decode_kernel(Etc1sDecodePa
                     uint32_t sym;
                     if (sel_rle > 0u) { sel_rle--; sym = num_selectors; }
                     else {
-                        sym = huff_decode(bs, W.win, l1s + 2 * kL1Size, P.flat[2], P.max_len[2], consumed);
+                        sym = huff_decode(bs, W.ring, hv[2], lane);
                         if (sym == 0xFFFFFFFFu) { err = ETC1S_ERR_HUFFMAN; break; }
                         if (sym == rle_sym) {
-                            const uint32_t r = huff_decode(bs, W.win, l1s + 3 * kL1Size, P.flat[3], P.max_len[3], consumed);
+                            const uint32_t r = huff_decode(bs, W.ring, hv[3], lane);
                             if (r == 0xFFFFFFFFu) { err = ETC1S_ERR_HUFFMAN; break; }
                             uint32_t cnt = 3u + r;
                             if (r == 63u) {
                                 uint32_t v;
-                                if (!vlc_decode(bs, W.win, 7, v, consumed)) { err = ETC1S_ERR_VLC; break; }
+                                if (!vlc_decode(bs, W.ring, 7, v)) { err = ETC1S_ERR_VLC; break; }
                                 cnt = 3u + v;
                             }
                             sel_rle = cnt - 1u;
@@ -185,18 +259,21 @@ __global__ void __launch_bounds__(128) etc1s_entropy_decode_kernel(Etc1sDecodePa
                         const uint32_t k = sym - num_selectors;
                         if (hist_size == 0u || k >= hist_size) { err = ETC1S_ERR_PREDICTION; break; }     // asserts mod.rs:404,409
                         sel = hist[k];
-                        if (k != 0u) { const uint16_t a = hist[k >> 1]; __syncwarp(); hist[k >> 1] = (uint16_t)sel; hist[k] = a; __syncwarp(); }
+                        if (k != 0u) { const uint16_t a = hist[k >> 1]; __syncwarp(); if (lane == 0) { hist[k >> 1] = (uint16_t)sel; hist[k] = a; } __syncwarp(); }
                     } else {
                         sel = sym;
-                        if (hist_size > 0u) { hist[rover] = (uint16_t)sym; rover++; if (rover == hist_size) rover = hist_size / 2; __syncwarp(); }
+                        if (hist_size > 0u) { if (lane == 0) hist[rover] = (uint16_t)sym; rover++; if (rover == hist_size) rover = hist_size / 2; __syncwarp(); }
                     }
                 } else sel = 0u;
                 if (ep >= num_endpoints || sel >= num_selectors) { err = ETC1S_ERR_RANGE; break; }        // asserts mod.rs:443-444
-                if (lane == 0) W.stage[b] = ep | (sel << 16);
+                if ((uint32_t)lane == b) mine = ep | (sel << 16);
             }
-            __syncwarp();
-            // ---- cooperative: flush the decoded pairs ----
-            if (!err && (uint32_t)lane < nb) out[(uint64_t)y * nbx + x0 + lane] = W.stage[lane];
+            // ---- cooperative: flush the decoded pairs, update the row state, land the prefetched ring piece ----
+            if (!err && (uint32_t)lane < nb) {
+                out[(uint64_t)y * nbx + x0 + lane] = mine;
+                rowep[x0 + lane] = (uint16_t)mine;
+            }
+            if (fetch) { piece_store(W.ring, loaded, lane, pre); loaded++; }
             __syncwarp();
         }
     }
@@ -272,13 +349,33 @@ __global__ void __launch_bounds__(256) etc1s_gather_rgba_kernel(const uint32_t* 
     }
 }
 
-size_t etc1s_decode_smem_bytes(int warps) { return 4 * kL1Size * sizeof(uint32_t) + (size_t)warps * sizeof(WarpShared); }
+// shared memory of K2: 4 first-level tables + sorted symbols + per warp {ring, history, previous-row state for row_cap blocks}
+static size_t etc1s_decode_smem_bytes(int warps, uint32_t row_cap, uint32_t sym_bytes)
+{
+    return 4 * kL1Size * sizeof(uint32_t) + sym_bytes + (size_t)warps * (sizeof(WarpShared) + ((size_t)row_cap + row_cap / 2 + 8) * 2);
+}
 
-cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, int warps_per_cta, cudaStream_t stream)
+cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, int warps_per_cta, uint32_t max_nbx, cudaStream_t stream)
 {
     if (P.num_slices == 0) return cudaSuccess;
+    const size_t limit = 220 * 1024;
+    // sorted symbols in shared memory when they fit in 96 KiB (codebooks up to ~24k entries each), else read from global
+    uint32_t sym_bytes = ((P.sym_ofs[4] * 2u) + 15u) & ~15u;
+    if (sym_bytes > 96 * 1024) sym_bytes = 0;
+    // previous-row state in shared memory when it fits, else in the scratch area
+    uint32_t row_cap = (max_nbx + 7u) & ~7u;
+    if (etc1s_decode_smem_bytes(1, row_cap, sym_bytes) > limit) row_cap = 0;
+    while (warps_per_cta > 1 && etc1s_decode_smem_bytes(warps_per_cta, row_cap, sym_bytes) > limit) warps_per_cta >>= 1;
+    static bool configured[16] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 16 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(etc1s_entropy_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
     const unsigned grid = (P.num_slices + warps_per_cta - 1) / warps_per_cta;
-    etc1s_entropy_decode_kernel<<<grid, 32 * warps_per_cta, etc1s_decode_smem_bytes(warps_per_cta), stream>>>(P);
+    etc1s_entropy_decode_kernel<<<grid, 32 * warps_per_cta, etc1s_decode_smem_bytes(warps_per_cta, row_cap, sym_bytes), stream>>>(P, row_cap, sym_bytes);
     return cudaGetLastError();
 }
 
