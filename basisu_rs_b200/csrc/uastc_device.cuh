@@ -660,6 +660,49 @@ B2BU_DI uint32_t q8(uint32_t v, uint32_t p)
     return q > 254u + p ? 254u + p : q;
 }
 
+// ---- SWAR helpers for the BC7 weight streams ----------------------------------------------
+// 8 fields of 2 bits (16 bits) -> 8 nibble-spaced fields (32 bits)
+B2BU_DI uint32_t spread2to4(uint32_t x)
+{
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    return (x | (x << 2)) & 0x33333333u;
+}
+// 8 fields of 3 bits (24 bits) -> 8 nibble-spaced fields (32 bits)
+B2BU_DI uint32_t spread3to4(uint32_t x)
+{
+    x = (x & 0x00000FFFu) | ((x & 0x00FFF000u) << 4);
+    x = (x & 0x003F003Fu) | ((x & 0x0FC00FC0u) << 2);
+    return (x & 0x07070707u) | ((x & 0x38383838u) << 1);
+}
+// the 8 two-bit fields at nibble positions of x (bits 4i, 4i+1) -> 16 contiguous bits
+B2BU_DI uint32_t compress4to2(uint32_t x)
+{
+    x &= 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    return (x | (x >> 8)) & 0x0000FFFFu;
+}
+
+// Output block as two 64-bit halves; every position below is a compile-time constant after unrolling.
+struct Out128 { uint64_t lo, hi; };
+B2BU_DI void emit(Out128& o, int pos, int len, uint32_t v)        // v < 2^len
+{
+    if (len <= 0) return;
+    if (pos + len <= 64) o.lo |= (uint64_t)v << pos;
+    else if (pos >= 64) o.hi |= (uint64_t)v << (pos - 64);
+    else { o.lo |= (uint64_t)v << pos; o.hi |= (uint64_t)v >> (64 - pos); }
+}
+B2BU_DI void emit64(Out128& o, int pos, uint64_t v)               // v already limited to the bits that fit
+{
+    if (pos >= 64) o.hi |= v << (pos - 64);
+    else if (pos == 0) o.lo |= v;
+    else { o.lo |= v << pos; o.hi |= v >> (64 - pos); }
+}
+
+// bc7.rs:9-310 for one (non void-extent) UASTC mode.  Endpoints travel as packed R|G<<8|B<<16|A<<24 words per
+// subset endpoint (permutation, anchor swaps and the 8-bit p-bit search work on whole words), weights as one
+// 64-bit stream per plane (width conversion, per-subset inversion and anchor-bit removal are SWAR).
 template <int M> B2BU_DI uint4 bc7_block(const uint4& b, const DevTables& T, uint32_t pat, uint32_t compsel)
 {
     using D = MD<M>;
@@ -667,50 +710,54 @@ template <int M> B2BU_DI uint4 bc7_block(const uint4& b, const DevTables& T, uin
     constexpr Bc7Info BI = bc7_info(BM);
     constexpr int bb = BI.weight_bits;
 
-    uint32_t e[D::N];
-    unpack_endpoints<M>(b, T, e);
-    // endpoint pairs per UASTC subset, channels R,G,B,A (uastc.rs:176-216)
-    uint32_t lo[3][4], hi[3][4];
+    // ---- endpoints per UASTC subset, packed (uastc.rs:176-216).  UASTC mode 2 keeps its 4-bit quantised values
+    // (v = 17 k): the shared p-bit LUTs of BC7 mode 1 are indexed by k
+    uint32_t plo[3] = {0u, 0u, 0u}, phi[3] = {0u, 0u, 0u};
+    {
+        uint32_t e[D::N];
+        if (BM == 1) { uint32_t d[D::N]; unpack_quant<M>(b, T, e, d); }
+        else unpack_endpoints<M>(b, T, e);
 #pragma unroll
-    for (int s = 0; s < 3; s++) {
-#pragma unroll
-        for (int c = 0; c < 4; c++) { lo[s][c] = c == 3 ? 255u : 0u; hi[s][c] = c == 3 ? 255u : 0u; }
-    }
-#pragma unroll
-    for (int s = 0; s < D::subsets; s++) {
-        const int o = s * D::NC * 2;
-        if (D::fmt == FMT_LA) {
-            lo[s][0] = lo[s][1] = lo[s][2] = e[o]; hi[s][0] = hi[s][1] = hi[s][2] = e[o + 1];
-            lo[s][3] = e[o + 2]; hi[s][3] = e[o + 3];
-        } else {
-#pragma unroll
-            for (int c = 0; c < D::NC; c++) { lo[s][c] = e[o + 2 * c]; hi[s][c] = e[o + 2 * c + 1]; }
+        for (int s = 0; s < D::subsets; s++) {
+            const int o = s * D::NC * 2;
+            if (D::fmt == FMT_LA) {
+                plo[s] = e[o] * 0x00010101u | (e[o + 2] << 24); phi[s] = e[o + 1] * 0x00010101u | (e[o + 3] << 24);
+            } else if (D::fmt == FMT_RGB) {
+                plo[s] = e[o] | (e[o + 2] << 8) | (e[o + 4] << 16) | 0xFF000000u; phi[s] = e[o + 1] | (e[o + 3] << 8) | (e[o + 5] << 16) | 0xFF000000u;
+            } else {
+                plo[s] = e[o] | (e[o + 2] << 8) | (e[o + 4] << 16) | (e[o + 6] << 24); phi[s] = e[o + 1] | (e[o + 3] << 8) | (e[o + 5] << 16) | (e[o + 7] << 24);
+            }
         }
     }
 
-    // weights per plane, converted to the BC7 width (bc7.rs:377-398)
+    // ---- weights: one bb-bit-per-texel stream per plane (bc7.rs:377-398) ----
     const uint4 U = uniform_weights<M>(b, T, pat);
-    uint32_t w[2][16];
+    uint64_t W0 = 0, W1 = 0;
+    if (D::planes == 1) {
+        if (D::wbits == bb) W0 = (uint64_t)U.x | ((uint64_t)U.y << 32);
+        else if (D::wbits == 2) {                                    // 2 -> 4 bits: x * 5
+            W0 = (uint64_t)(spread2to4(U.x & 0xFFFFu) * 5u) | ((uint64_t)(spread2to4(U.x >> 16) * 5u) << 32);
+        } else if (D::wbits == 3) {                                  // 3 -> 4 bits: 2x + (x >> 2)
+            const uint32_t x0 = spread3to4(U.x & 0xFFFFFFu), x1 = spread3to4(getbits(U, 24, 24));
+            W0 = (uint64_t)(2u * x0 + ((x0 >> 2) & 0x11111111u)) | ((uint64_t)(2u * x1 + ((x1 >> 2) & 0x11111111u)) << 32);
+        } else {                                                     // 5 -> 4 bits: LUT
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-#pragma unroll
-        for (int p = 0; p < D::planes; p++) {
-            uint32_t x = getbits(U, (i * D::planes + p) * D::wbits, D::wbits);
-            if (D::wbits == 1 && bb == 2) x = x * 3u;
-            else if (D::wbits == 2 && bb == 4) x = x * 5u;
-            else if (D::wbits == 3 && bb == 4) x = 2u * x + (x >> 2);
-            else if (D::wbits == 5 && bb == 4) x = T.w5to4[x];
-            w[p][i] = x;
+            for (int i = 0; i < 16; i++) W0 |= (uint64_t)T.w5to4[getbits(U, 5 * i, 5)] << (4 * i);
         }
+    } else if (D::wbits == 1) {                                      // texel-major, plane-minor; 1 -> 2 bits: x * 3
+        W0 = (uint64_t)((U.x & 0x55555555u) * 3u);
+        W1 = (uint64_t)(((U.x >> 1) & 0x55555555u) * 3u);
+    } else {                                                         // two planes of 2-bit weights, de-interleaved
+        W0 = (uint64_t)(compress4to2(U.x) | (compress4to2(U.y) << 16));
+        W1 = (uint64_t)(compress4to2(U.x >> 2) | (compress4to2(U.y >> 2) << 16));
     }
 
-    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    Out128 out;
+    out.lo = 1ull << BM; out.hi = 0;
     int pos = BM + 1;
-    out.x = 1u << BM;
 
     uint32_t a1 = 0, a2 = 0;          // BC7 anchors of subsets 1, 2
-    // BC7-side endpoints per BC7 subset
-    uint32_t elo[3][4], ehi[3][4];
+    uint32_t qlo[3], qhi[3];          // endpoints per BC7 subset
     if (BI.subsets > 1) {
         // bc7.rs:113-198: partition index, subset permutation, anchor-MSB fix-up
         uint32_t info, bpw;
@@ -718,90 +765,87 @@ template <int M> B2BU_DI uint4 bc7_block(const uint4& b, const DevTables& T, uin
         else if (M == 7) { info = T.bc7p23[pat]; bpw = T.bc7pat23[pat]; }
         else if (D::subsets == 2) { info = T.bc7p2[pat]; bpw = T.bc7pat2[pat]; }
         else { info = T.bc7p3[pat]; bpw = T.bc7pat3[pat]; }
-        putbits(out, pos, BI.pat_bits, info & 63u);
+        emit(out, pos, BI.pat_bits, info & 63u);
         pos += BI.pat_bits;
         a1 = (info >> 16) & 15u; a2 = (info >> 20) & 15u;
 #pragma unroll
         for (int s = 0; s < BI.subsets; s++) {
             const uint32_t src = (info >> (8 + 2 * s)) & 3u;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                uint32_t l = lo[0][c], h = hi[0][c];
-                if (D::subsets >= 2) { if (src == 1u) { l = lo[1][c]; h = hi[1][c]; } }
-                if (D::subsets >= 3) { if (src == 2u) { l = lo[2][c]; h = hi[2][c]; } }
-                elo[s][c] = l; ehi[s][c] = h;
-            }
+            uint32_t l = plo[0], h = phi[0];
+            if (D::subsets >= 2) { if (src == 1u) { l = plo[1]; h = phi[1]; } }
+            if (D::subsets >= 3) { if (src == 2u) { l = plo[2]; h = phi[2]; } }
+            qlo[s] = l; qhi[s] = h;
         }
-        // which BC7 subsets have an anchor weight with its MSB set
-        bool invs[3];
-        uint32_t wa0 = w[0][0], wa1 = 0, wa2 = 0;
+        // a BC7 subset whose anchor weight has its MSB set swaps its endpoints and inverts its weights
+        const bool inv0 = (W0 >> (bb - 1)) & 1ull;
+        const bool inv1 = (W0 >> (a1 * bb + bb - 1)) & 1ull;
+        const bool inv2 = BI.subsets == 3 ? (bool)((W0 >> (a2 * bb + bb - 1)) & 1ull) : false;
+        const bool invs[3] = {inv0, inv1, inv2};
 #pragma unroll
-        for (int i = 0; i < 16; i++) { if ((uint32_t)i == a1) wa1 = w[0][i]; if ((uint32_t)i == a2) wa2 = w[0][i]; }
-        invs[0] = (wa0 >> (bb - 1)) & 1u; invs[1] = (wa1 >> (bb - 1)) & 1u; invs[2] = BI.subsets == 3 ? ((wa2 >> (bb - 1)) & 1u) : false;
+        for (int s = 0; s < BI.subsets; s++) { const uint32_t l = qlo[s], h = qhi[s]; qlo[s] = invs[s] ? h : l; qhi[s] = invs[s] ? l : h; }
+        if (bb == 2) {
+            uint32_t x = 0;
 #pragma unroll
-        for (int s = 0; s < BI.subsets; s++) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const uint32_t l = elo[s][c], h = ehi[s][c];
-                elo[s][c] = invs[s] ? h : l; ehi[s][c] = invs[s] ? l : h;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const uint32_t s = (bpw >> (2 * i)) & 3u;
-            const bool iv = s == 0u ? invs[0] : s == 1u ? invs[1] : invs[2];
-            if (iv) w[0][i] = (~w[0][i]) & ((1u << bb) - 1u);
+            for (int s = 0; s < BI.subsets; s++) if (invs[s]) x |= subset_mask2(bpw, (uint32_t)s);
+            W0 ^= (uint64_t)x;
+        } else {
+            // UASTC mode 2 -> BC7 mode 1 (3-bit weights, 2 subsets): the BC7 map is the UASTC map or its complement
+            const uint64_t full = 0xFFFFFFFFFFFFull, u1 = T.pat2w3[pat];
+            const uint64_t m1 = ((info >> 8) & 3u) == 0u ? u1 : (~u1 & full);
+            uint64_t x = 0;
+            if (inv0) x |= ~m1 & full;
+            if (inv1) x |= m1;
+            W0 ^= x;
         }
     } else {
-#pragma unroll
-        for (int c = 0; c < 4; c++) { elo[0][c] = lo[0][c]; ehi[0][c] = hi[0][c]; }
+        qlo[0] = plo[0]; qhi[0] = phi[0];
         if (D::planes == 2) {
             // bc7.rs:207-246: rotate the dual-plane channel into alpha.  The "anchor MSB set" branches
             // (:200-205, :208-236) are dead: UASTC anchors carry no MSB and every width LUT keeps them low.
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const uint32_t l = elo[0][c], h = ehi[0][c];
-                const bool sw = compsel == (uint32_t)c;
-                elo[0][c] = sw ? elo[0][3] : l; ehi[0][c] = sw ? ehi[0][3] : h;
-                elo[0][3] = sw ? l : elo[0][3]; ehi[0][3] = sw ? h : ehi[0][3];
-            }
-            putbits(out, pos, 2, (compsel + 1u) & 3u);
+            const uint32_t sel = compsel == 0u ? 0x0213u : compsel == 1u ? 0x1230u : compsel == 2u ? 0x2310u : 0x3210u;
+            qlo[0] = __byte_perm(qlo[0], 0u, sel); qhi[0] = __byte_perm(qhi[0], 0u, sel);
+            emit(out, pos, 2, (compsel + 1u) & 3u);
             pos += 2;
         }
     }
 
-    // endpoint re-quantisation (bc7.rs:249-273)
+    // ---- endpoint re-quantisation (bc7.rs:249-273): after this block every byte of q* is the field to write ----
     uint32_t pb[3][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}};
-    if (BI.p_bits) {
+    if (BI.p_bits && BI.color_bits == 7) {
+        // 8 total bits (bc7.rs:478-553 in integers): the error of p is the number of channels whose parity differs from
+        // p, so p = 1 iff more than half of the channels are odd; then field = p ? v >> 1 : min((v + 1) >> 1, 127)
+        constexpr uint32_t CH1 = BI.channels == 3 ? 0x00010101u : 0x01010101u;
 #pragma unroll
         for (int s = 0; s < BI.subsets; s++) {
-            if (BI.color_bits == 7) {
-                // 8 total bits: error of p is the number of channels whose parity differs from p
-                uint32_t odd_l = 0, odd_h = 0;
 #pragma unroll
-                for (int c = 0; c < BI.channels; c++) { odd_l += elo[s][c] & 1u; odd_h += ehi[s][c] & 1u; }
-                // err0 = #odd (+ v==255 counts as odd already), err1 = #even; p=1 iff err1 < err0
-                const uint32_t pl = (BI.channels - odd_l) < odd_l ? 1u : 0u;
-                const uint32_t ph = (BI.channels - odd_h) < odd_h ? 1u : 0u;
+            for (int k = 0; k < 2; k++) {
+                const uint32_t x = k ? qhi[s] : qlo[s];
+                const uint32_t odd = (uint32_t)__popc(x & CH1);
+                const uint32_t p = (2u * odd > (uint32_t)BI.channels) ? 1u : 0u;
+                uint32_t q = ((x >> 1) & 0x7F7F7F7Fu) + (p ? 0u : (x & 0x01010101u));
+                q -= (q >> 7) & 0x01010101u;
+                if (k) qhi[s] = q; else qlo[s] = q;
+                pb[s][k] = p;
+            }
+        }
+    } else if (BI.p_bits) {
+        // 6 total bits (BC7 mode 7): LUTs of the exact squared error of both p and of the quantised value
 #pragma unroll
-                for (int c = 0; c < 4; c++) { elo[s][c] = q8(elo[s][c], pl) >> 1; ehi[s][c] = q8(ehi[s][c], ph) >> 1; }
-                pb[s][0] = pl; pb[s][1] = ph;
-            } else {
-                // 6 total bits (BC7 mode 7): LUT of quantised value and exact squared error
-                uint32_t el0 = 0, el1 = 0, eh0 = 0, eh1 = 0;
+        for (int s = 0; s < BI.subsets; s++) {
 #pragma unroll
-                for (int c = 0; c < BI.channels; c++) {
-                    el0 += T.pe6[0][elo[s][c]]; el1 += T.pe6[1][elo[s][c]];
-                    eh0 += T.pe6[0][ehi[s][c]]; eh1 += T.pe6[1][ehi[s][c]];
-                }
-                const uint32_t pl = el1 < el0 ? 1u : 0u, ph = eh1 < eh0 ? 1u : 0u;
-#pragma unroll
-                for (int c = 0; c < 4; c++) { elo[s][c] = T.pq6[pl][elo[s][c]] >> 1; ehi[s][c] = T.pq6[ph][ehi[s][c]] >> 1; }
-                pb[s][0] = pl; pb[s][1] = ph;
+            for (int k = 0; k < 2; k++) {
+                const uint32_t x = k ? qhi[s] : qlo[s];
+                const uint32_t c0 = x & 0xFFu, c1 = (x >> 8) & 0xFFu, c2 = (x >> 16) & 0xFFu, c3 = x >> 24;
+                const uint32_t esum = T.pe6p[c0] + T.pe6p[c1] + T.pe6p[c2] + T.pe6p[c3];       // err(p=0) | err(p=1) << 16, each < 2^14
+                const uint32_t p = (esum >> 16) < (esum & 0xFFFFu) ? 1u : 0u;
+                const uint8_t* tq = T.pq6[p];
+                const uint32_t q = (uint32_t)(tq[c0] >> 1) | ((uint32_t)(tq[c1] >> 1) << 8) | ((uint32_t)(tq[c2] >> 1) << 16) | ((uint32_t)(tq[c3] >> 1) << 24);
+                if (k) qhi[s] = q; else qlo[s] = q;
+                pb[s][k] = p;
             }
         }
     } else if (BI.sp_bits) {
-        // BC7 mode 1 <= UASTC mode 2: endpoints are 17*k; f32 terms from the LUT, summed in the reference's order
+        // BC7 mode 1 <= UASTC mode 2: bytes hold k (endpoint = 17 k); f32 terms from the LUT, summed in the reference's order
 #pragma unroll
         for (int s = 0; s < BI.subsets; s++) {
             float err[2];
@@ -810,49 +854,57 @@ template <int M> B2BU_DI uint4 bc7_block(const uint4& b, const DevTables& T, uin
                 float acc = 0.f;
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    const float t = __fadd_rn(__uint_as_float(T.se7_bits[p][elo[s][c] / 17u]), __uint_as_float(T.se7_bits[p][ehi[s][c] / 17u]));
+                    const float t = __fadd_rn(__uint_as_float(T.se7_bits[p][(qlo[s] >> (8 * c)) & 0xFFu]), __uint_as_float(T.se7_bits[p][(qhi[s] >> (8 * c)) & 0xFFu]));
                     acc = __fadd_rn(acc, t);
                 }
                 err[p] = acc;
             }
             const uint32_t p = err[1] < err[0] ? 1u : 0u;
+            const uint8_t* tq = T.sq7[p];
+            uint32_t l = 0, h = 0;
 #pragma unroll
-            for (int c = 0; c < 3; c++) { elo[s][c] = T.sq7[p][elo[s][c] / 17u] >> 1; ehi[s][c] = T.sq7[p][ehi[s][c] / 17u] >> 1; }
+            for (int c = 0; c < 3; c++) {
+                l |= (uint32_t)(tq[(qlo[s] >> (8 * c)) & 0xFFu] >> 1) << (8 * c);
+                h |= (uint32_t)(tq[(qhi[s] >> (8 * c)) & 0xFFu] >> 1) << (8 * c);
+            }
+            qlo[s] = l; qhi[s] = h;
             pb[s][0] = p; pb[s][1] = p;
         }
     } else {
+        // no p-bits: (e * (2^bits - 1) + 127) / 255 from the LUTs; BC7 mode 5 keeps its 8-bit alpha
+        const uint8_t* tq = BI.color_bits == 5 ? T.q5 : T.q7;
 #pragma unroll
         for (int s = 0; s < BI.subsets; s++) {
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const uint32_t mk = (1u << (c == 3 ? BI.alpha_bits : BI.color_bits)) - 1u;
-                elo[s][c] = (elo[s][c] * mk + 127u) / 255u; ehi[s][c] = (ehi[s][c] * mk + 127u) / 255u;
+            for (int k = 0; k < 2; k++) {
+                const uint32_t x = k ? qhi[s] : qlo[s];
+                uint32_t q = (uint32_t)tq[x & 0xFFu] | ((uint32_t)tq[(x >> 8) & 0xFFu] << 8) | ((uint32_t)tq[(x >> 16) & 0xFFu] << 16);
+                if (BI.channels == 4) q |= x & 0xFF000000u;
+                if (k) qhi[s] = q; else qlo[s] = q;
             }
         }
     }
 
-    // bc7.rs:276-307: endpoints channel-major, p-bits, weights
+    // ---- bc7.rs:276-307: endpoints channel-major, p-bits, weights ----
 #pragma unroll
     for (int c = 0; c < BI.channels; c++) {
         const int nb = c == 3 ? BI.alpha_bits : BI.color_bits;
 #pragma unroll
         for (int s = 0; s < BI.subsets; s++) {
-            putbits(out, pos, nb, elo[s][c]); pos += nb;
-            putbits(out, pos, nb, ehi[s][c]); pos += nb;
+            emit(out, pos, nb, (qlo[s] >> (8 * c)) & 0xFFu); pos += nb;
+            emit(out, pos, nb, (qhi[s] >> (8 * c)) & 0xFFu); pos += nb;
         }
     }
     if (BI.p_bits) {
 #pragma unroll
-        for (int s = 0; s < BI.subsets; s++) { putbits(out, pos, 2, (pb[s][1] << 1) | pb[s][0]); pos += 2; }
+        for (int s = 0; s < BI.subsets; s++) { emit(out, pos, 2, (pb[s][1] << 1) | pb[s][0]); pos += 2; }
     } else if (BI.sp_bits) {
-        putbits(out, pos, 2, (pb[1][0] << 1) | pb[0][0]); pos += 2;
+        emit(out, pos, 2, (pb[1][0] << 1) | pb[0][0]); pos += 2;
     }
-    // weights: build the uniform bb-bit stream per plane, then drop the anchors' MSB (always 0 by now)
+    // weights: drop the anchors' MSB (always 0 by now), highest position first
 #pragma unroll
     for (int p = 0; p < BI.planes; p++) {
-        uint64_t ws = 0;
-#pragma unroll
-        for (int i = 0; i < 16; i++) ws |= (uint64_t)w[p][i] << (bb * i);
+        uint64_t ws = p ? W1 : W0;
         if (BI.subsets == 3) {
             const uint32_t ahi = a1 > a2 ? a1 : a2, alo = a1 > a2 ? a2 : a1;
             ws = delete_bit<uint64_t>(ws, ahi * bb + bb - 1);
@@ -861,10 +913,10 @@ template <int M> B2BU_DI uint4 bc7_block(const uint4& b, const DevTables& T, uin
             ws = delete_bit<uint64_t>(ws, a1 * bb + bb - 1);
         }
         ws = delete_bit<uint64_t>(ws, bb - 1);
-        out = or128(out, shl128(u64_to_128(ws), pos));
+        emit64(out, pos, ws);
         pos += 16 * bb - BI.subsets;
     }
-    return out;
+    return make_uint4((uint32_t)out.lo, (uint32_t)(out.lo >> 32), (uint32_t)out.hi, (uint32_t)(out.hi >> 32));
 }
 
 // ------------------------------------------------------------------------------------------

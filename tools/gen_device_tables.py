@@ -153,6 +153,9 @@ def main():
     out.append("  /* sq7 */ {{%s},{%s}},\n" % (",".join(map(str, sq7[0])), ",".join(map(str, sq7[1]))))
     out.append("  /* se7_bits */ {{%s},{%s}},\n" % (",".join("0x%08Xu" % v for v in se7[0]), ",".join("0x%08Xu" % v for v in se7[1])))
     out.append(carr("w5to4", [0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 6, 7, 8, 9, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 14, 14, 15, 15]))
+    out.append(carr("pe6p", ["0x%08Xu" % (pe6[0][v] | (pe6[1][v] << 16)) for v in range(256)]))
+    out.append(carr("q5", [(v * 31 + 127) // 255 for v in range(256)]))      # bc7.rs:264-271 without p-bits, 5 bits
+    out.append(carr("q7", [(v * 127 + 127) // 255 for v in range(256)]))     # 7 bits
     etc1_mod = [[-8, -2, 2, 8], [-17, -5, 5, 17], [-29, -9, 9, 29], [-42, -13, 13, 42], [-60, -18, 18, 60],
                 [-80, -24, 24, 80], [-106, -33, 33, 106], [-183, -47, 47, 183]]
     eac = [[-3, -6, -9, -15, 2, 5, 8, 14], [-3, -7, -10, -13, 2, 6, 9, 12], [-2, -5, -8, -13, 1, 4, 7, 12],
