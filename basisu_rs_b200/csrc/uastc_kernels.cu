@@ -128,11 +128,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"     // %2: suspend-time hint, the thread sleeps until the phase flips
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
 {
@@ -178,6 +178,7 @@ __device__ unsigned long long g_trace[160][64];
 template <int TARGET> struct PipeCfg {
     static constexpr int OB = TARGET == TGT_RGBA ? 64 : TARGET == TGT_ETC1 ? 8 : 16;
     static constexpr bool IN_PLACE = OB == 16;
+    static constexpr bool DYNAMIC = TARGET != TGT_ASTC;
     static constexpr int TILE = TARGET == TGT_RGBA ? B2BU_TILE_RGBA : B2BU_TILE16;
     static constexpr int SORT_WARPS = B2BU_SORT_WARPS;
     static constexpr int SORT_THREADS = SORT_WARPS * 32;
@@ -201,16 +202,17 @@ template <int TARGET> struct PipeCfg {
 };
 
 // contiguous, 32-block aligned share of CTA c out of G
-__device__ __forceinline__ uint64_t cta_range_start(uint64_t nblocks, uint32_t c, uint32_t G)
+// (quot, rem) = (nblocks / G, nblocks % G) come from the host
+__device__ __forceinline__ uint64_t cta_range_start(uint64_t nblocks, uint64_t quot, uint32_t rem, uint32_t c, uint32_t G)
 {
     if (c >= G) return nblocks;
-    return ((nblocks / G) * c + (nblocks % G) * c / G) & ~31ull;
+    return (quot * c + rem * c / G) & ~31ull;
 }
 
 template <int TARGET>
 __global__ void __launch_bounds__(PipeCfg<TARGET>::THREADS, 1)
 uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64_t nblocks, uint32_t blocks_per_row,
-                    uint64_t index_base, unsigned long long* __restrict__ err)
+                    uint64_t index_base, unsigned long long* __restrict__ err, uint64_t range_quot, uint32_t range_rem)
 {
     using C = PipeCfg<TARGET>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -228,8 +230,8 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // this CTA's contiguous block range, cut into equal tiles of at most TILE blocks (multiples of 32)
-    const uint64_t r0 = cta_range_start(nblocks, blockIdx.x, gridDim.x);
-    const uint64_t r1 = cta_range_start(nblocks, blockIdx.x + 1, gridDim.x);
+    const uint64_t r0 = cta_range_start(nblocks, range_quot, range_rem, blockIdx.x, gridDim.x);
+    const uint64_t r1 = cta_range_start(nblocks, range_quot, range_rem, blockIdx.x + 1, gridDim.x);
     const uint32_t rlen = (uint32_t)(r1 - r0);
     // tile k covers [tile_start(k), tile_start(k + 1)) of the range.  The first two tiles are short (TILE/4, TILE/2)
     // so that the workers start early; the rest of the range is cut into equal tiles of at most TILE blocks.
@@ -331,9 +333,9 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
             uint32_t mr[C::PERS];
 #pragma unroll
             for (int j = 0; j < C::PERS; j++) {
-                const uint32_t idx = st + j * C::SORT_THREADS;
+                // blocks past the end of a short tile read stale slot contents (always inside the slot); they are discarded below
                 mr[j] = 31u;
-                if (j < jmax) mr[j] = tin[idx < nt ? idx : nt - 1u].x & 127u;
+                if (j < jmax) mr[j] = tin[st + j * C::SORT_THREADS].x & 127u;
             }
 #pragma unroll
             for (int j = 0; j < C::PERS; j++) {
@@ -417,10 +419,16 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
 #endif
         mbar_wait(&bar_full[s], u & 1u);          // completed long ago: observes the bulk-copied bytes directly
         const uint32_t nitems = ctl[s * 4 + 1];
-        for (;;) {
-            uint32_t item = 0;
-            if (lane == 0) item = atom_add_shared(&ctl[s * 4 + 0], 1u);
-            item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        // Items are pulled in bin order from a shared counter.  Besides balancing uneven items this keeps every worker of
+        // the SM inside the same few modes, i.e. the same few KB of code: dealing the items round-robin instead let the
+        // warps drift apart and ran the large-code targets (ETC1/ETC2) 3x slower on instruction-cache misses.  ASTC's
+        // code is small enough for the static deal to win (no counter round trip per item).
+        for (uint32_t it = (uint32_t)warp;; it += C::WORK_WARPS) {
+            uint32_t item = it;
+            if (C::DYNAMIC) {
+                if (lane == 0) item = atom_add_shared(&ctl[s * 4 + 0], 1u);
+                item = __shfl_sync(0xFFFFFFFFu, item, 0);
+            }
             if (item >= nitems) break;
             const uint32_t inf_w = inf[item];
             const uint32_t mode = inf_w & 0xFFu;
@@ -466,7 +474,7 @@ static cudaError_t launch_sorted(const uint4* in, void* d_out, uint64_t nblocks,
     // one persistent CTA per SM; fewer when the input is small (at least ~one half tile each)
     const uint64_t want = (nblocks + C::TILE / 2 - 1) / (C::TILE / 2);
     const unsigned grid = (unsigned)(want < (uint64_t)sm_count ? want : (uint64_t)sm_count);
-    uastc_sorted_kernel<TARGET><<<grid, C::THREADS, C::SMEM, stream>>>(in, d_out, nblocks, bpr, index_base, d_err);
+    uastc_sorted_kernel<TARGET><<<grid, C::THREADS, C::SMEM, stream>>>(in, d_out, nblocks, bpr, index_base, d_err, nblocks / grid, (uint32_t)(nblocks % grid));
     return cudaGetLastError();
 }
 
