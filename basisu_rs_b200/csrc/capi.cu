@@ -8,6 +8,7 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "../../include/b2bu.h"
 #include "host_internal.h"
@@ -43,7 +44,12 @@ int get_ctx(DeviceCtx** out)
         c.device = dev;
         c.sm_count = prop.multiProcessorCount;
         CK(upload_tables());
-        for (int i = 0; i < kStreams; i++) CK(cudaStreamCreateWithFlags(&c.streams[i], cudaStreamNonBlocking));
+        for (int i = 0; i < kStreams; i++) {
+            CK(cudaStreamCreateWithFlags(&c.streams[i], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&c.ev_h2d[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c.ev_kernel[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c.ev_d2h[i], cudaEventDisableTiming));
+        }
         CK(cudaMalloc(&c.d_err, sizeof(unsigned long long)));
         CK(cudaMallocHost(&c.h_err, sizeof(unsigned long long)));
         c.ready = true;
@@ -91,23 +97,46 @@ static int uastc_host_run(int target, const uint8_t* blocks, size_t nblocks, siz
         if ((st = ensure(&c->d_in[s], &c->in_cap[s], chunk * 16))) return st;
         if ((st = ensure(&c->d_out[s], &c->out_cap[s], chunk * ob))) return st;
     }
-    CK(cudaMemsetAsync(c->d_err, 0xFF, sizeof(unsigned long long), c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[0]));
+    // chunk schedule: the first H2D copy and the last D2H copy cannot overlap with anything, so the pipeline ramps
+    // up (chunk/8, /4, /2), runs full-size chunks, and ramps down again (/2, /4, /8)
+    const size_t unit = target == B2BU_RGBA ? bpr : 1;              // RGBA chunks are whole block rows
+    std::vector<size_t> sched;
+    {
+        const size_t ramp[3] = {std::max(chunk >> 3, unit) / unit * unit, std::max(chunk >> 2, unit) / unit * unit, std::max(chunk >> 1, unit) / unit * unit};
+        const size_t ramp_total = ramp[0] + ramp[1] + ramp[2];
+        size_t left = nblocks;
+        if (nblocks > 2 * ramp_total) {
+            for (int k = 0; k < 3; k++) { sched.push_back(ramp[k]); left -= ramp[k]; }
+            while (left > ramp_total) { const size_t n = std::min(chunk, left - ramp_total); sched.push_back(n); left -= n; }
+            for (int k = 2; k >= 0 && left; k--) { const size_t n = k ? std::min(ramp[k], left) : left; sched.push_back(n); left -= n; }
+        } else {
+            while (left) { const size_t n = std::min(ramp[1], left); sched.push_back(n); left -= n; }
+        }
+    }
+    // Three streams, one per engine (H2D copies, kernels, D2H copies), chained per buffer slot with events: the copy
+    // engines always have the next transfer queued and no transfer waits behind an unrelated one of the other direction.
+    cudaStream_t sH = c->streams[0], sK = c->streams[1], sD = c->streams[2];
+    CK(cudaMemsetAsync(c->d_err, 0xFF, sizeof(unsigned long long), sK));
     size_t done = 0;
     int ci = 0;
-    while (done < nblocks) {
-        const size_t n = nblocks - done < chunk ? nblocks - done : chunk;
+    for (const size_t n : sched) {
         const int s = ci % kStreams;
-        cudaStream_t stream = c->streams[s];
-        CK(cudaMemcpyAsync(c->d_in[s], blocks + done * 16, n * 16, cudaMemcpyHostToDevice, stream));
-        CK(launch_uastc_transcode(target, c->d_in[s], c->d_out[s], n, (uint32_t)bpr, done, c->d_err, c->sm_count, stream));
+        if (ci >= kStreams) CK(cudaStreamWaitEvent(sH, c->ev_kernel[s], 0));      // the kernel that read d_in[s] has finished
+        CK(cudaMemcpyAsync(c->d_in[s], blocks + done * 16, n * 16, cudaMemcpyHostToDevice, sH));
+        CK(cudaEventRecord(c->ev_h2d[s], sH));
+        CK(cudaStreamWaitEvent(sK, c->ev_h2d[s], 0));
+        if (ci >= kStreams) CK(cudaStreamWaitEvent(sK, c->ev_d2h[s], 0));         // the copy that read d_out[s] has finished
+        CK(launch_uastc_transcode(target, c->d_in[s], c->d_out[s], n, (uint32_t)bpr, done, c->d_err, c->sm_count, sK));
         count_launch(1);
-        CK(cudaMemcpyAsync(out + done * ob, c->d_out[s], n * ob, cudaMemcpyDeviceToHost, stream));
+        CK(cudaEventRecord(c->ev_kernel[s], sK));
+        CK(cudaStreamWaitEvent(sD, c->ev_kernel[s], 0));
+        CK(cudaMemcpyAsync(out + done * ob, c->d_out[s], n * ob, cudaMemcpyDeviceToHost, sD));
+        CK(cudaEventRecord(c->ev_d2h[s], sD));
         done += n;
         ci++;
     }
-    for (int s = 0; s < kStreams; s++) CK(cudaStreamSynchronize(c->streams[s]));
-    CK(cudaMemcpy(c->h_err, c->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sD));   // after the last kernel (sD waited on it)
+    CK(cudaStreamSynchronize(sD));
     return decode_status_word(*c->h_err, first_bad);
 }
 

@@ -7,8 +7,14 @@
 namespace b2bu {
 
 constexpr int kMaxDevices = 16;
-constexpr int kStreams = 3;                      // H2D / kernel / D2H of consecutive chunks overlap
-constexpr size_t kChunkBlocks = size_t(1) << 19; // 8 MiB of UASTC per pipeline stage
+#ifndef B2BU_STREAMS
+#define B2BU_STREAMS 4
+#endif
+#ifndef B2BU_CHUNK_LOG2
+#define B2BU_CHUNK_LOG2 19
+#endif
+constexpr int kStreams = B2BU_STREAMS;           // buffer slots of the host-pointer pipeline; streams[0..2] = H2D, kernels, D2H
+constexpr size_t kChunkBlocks = size_t(1) << B2BU_CHUNK_LOG2; // 16 B << 19 = 8 MiB of UASTC per pipeline stage
 
 enum { ERR_MODE_DEV = 2, ERR_PATTERN_DEV = 3 };  // == ERR_MODE / ERR_PATTERN in uastc_device.cuh
 
@@ -21,6 +27,7 @@ struct DeviceCtx {
     size_t in_cap[kStreams] = {};
     void* d_out[kStreams] = {};
     size_t out_cap[kStreams] = {};
+    cudaEvent_t ev_h2d[kStreams] = {}, ev_kernel[kStreams] = {}, ev_d2h[kStreams] = {};   // per buffer slot
     unsigned long long* d_err = nullptr;          // one status word, atomicMin'ed by every launch of a call
     unsigned long long* h_err = nullptr;          // pinned
 };
