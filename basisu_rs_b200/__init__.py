@@ -79,6 +79,7 @@ def lib() -> ctypes.CDLL:
     L.b2bu_uastc_transcode_dev.argtypes = [c.c_int, c.c_void_p, sz, sz, c.c_void_p, sz, c.c_void_p, c.c_void_p]
     L.b2bu_status_reset_dev.argtypes = [c.c_void_p, c.c_void_p]
     L.b2bu_status_read_dev.argtypes = [c.c_void_p, c.c_void_p, u64p]
+    L.b2bu_probe_int_peak.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_double)]
     L.b2bu_launch_count.restype = c.c_uint64
     L.b2bu_etc1s_open.argtypes = [c.c_uint32, c.c_uint32, u8p, sz, u8p, sz, u8p, sz, c.c_int, c.POINTER(c.c_void_p)]
     L.b2bu_etc1s_close.argtypes = [c.c_void_p]

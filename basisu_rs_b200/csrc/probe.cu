@@ -1,0 +1,71 @@
+// Integer-issue probe (measurement aid behind b2bu_probe_int_peak): streams of independent LOP3 / SHF
+// (alu pipe) and IMAD (fma pipe) instructions, timed with CUDA events.  north_star defines the roofline of
+// this path as the slower of bytes / HBM bandwidth and integer ops / INT throughput; this measures the
+// second denominator on the device the library runs on.
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/b2bu.h"
+#include "host_internal.h"
+
+namespace b2bu {
+
+template <int MIX>   // 0: alu pipe only, 1: alternate alu / fma pipe
+__global__ void __launch_bounds__(1024) int_probe_kernel(uint32_t* out, uint32_t iters, uint32_t seed)
+{
+    uint32_t a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = seed + threadIdx.x * 8u + i;
+    const uint32_t k1 = seed | 1u, k2 = seed * 3u + 7u;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                a[i] = (a[i] ^ k1) & (a[(i + 1) & 7] | k2);      // LOP3
+                if (MIX) a[i] = a[i] * k1 + k2;                  // IMAD
+                else a[i] = __funnelshift_l(a[i], a[(i + 3) & 7], 7);   // SHF (an integer add would be issued as IMAD.IADD on the fma pipe)
+            }
+        }
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x ^= a[i];
+    if (x == 0x12345u) out[0] = x;            // keeps the chain alive, practically never taken
+}
+
+}  // namespace b2bu
+
+using namespace b2bu;
+
+extern "C" int b2bu_probe_int_peak(double* alu_tops, double* mixed_tops)
+{
+    DeviceCtx* c;
+    int st = get_ctx(&c);
+    if (st) return st;
+    uint32_t* d = nullptr;
+    if (cudaMalloc(&d, 4) != cudaSuccess) return B2BU_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const uint32_t iters = 4096;
+    const unsigned grid = (unsigned)c->sm_count * 2;
+    double res[2] = {0, 0};
+    for (int mix = 0; mix < 2; mix++) {
+        for (int rep = 0; rep < 3; rep++) {
+            cudaEventRecord(e0, c->streams[1]);
+            if (mix) int_probe_kernel<1><<<grid, 1024, 0, c->streams[1]>>>(d, iters, 12345u + rep);
+            else int_probe_kernel<0><<<grid, 1024, 0, c->streams[1]>>>(d, iters, 12345u + rep);
+            cudaEventRecord(e1, c->streams[1]);
+            if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return B2BU_ERR_CUDA; }
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            const double ops = (double)grid * 1024.0 * iters * 4 * 8 * 2;          // thread-level integer instructions
+            const double tops = ops / (ms * 1e-3) / 1e12;
+            if (tops > res[mix]) res[mix] = tops;
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    if (alu_tops) *alu_tops = res[0];
+    if (mixed_tops) *mixed_tops = res[1];
+    return B2BU_OK;
+}

@@ -32,6 +32,7 @@ import numpy as np
 TARGET_NAMES = {"rgba": 0, "astc": 1, "bc7": 2, "etc1": 3, "etc2": 4}
 OUT_BYTES = {0: 64, 1: 16, 2: 16, 3: 8, 4: 16}
 ALGO_BYTES = {0: 80, 1: 32, 2: 32, 3: 24, 4: 32}          # input + output per block
+INT_OPS = {0: 400, 1: 300, 2: 550, 3: 800, 4: 1300}        # algorithmic integer ops per block
 
 
 def make_payload(kind: str, nblocks: int, seed: int = 0) -> np.ndarray:
@@ -294,10 +295,84 @@ def bench_c4_etc1s(L, b, nb=1024, slices=64, n_cb=4096, reps=2):
     return res
 
 
+def bench_c5_mixed_batch(L, b, torch, dist, rank, world, payload, total_images, status, sh):
+    """configs[4]: a batch of mixed UASTC / ETC1S 2048x2048 textures sharded by image over the ranks (image i -> rank i mod world,
+    basisu_rs_b200.shard.plan_shards), no collective on the data path.  UASTC images go to RGBA and BC7 through the device-resident
+    entry point (one launch per image); ETC1S images go to RGBA (the reference has no ETC1S -> BC7) through b2bu_etc1s_transcode_slices,
+    whose device phases (K2 + K3) are timed by the library.  BASELINE names 4096 images; the default measures `total_images` of them."""
+    import etc1s_common as ec
+    from etc1s_synth import encode, make_codebooks, make_indices
+    from basisu_rs_b200.shard import plan_shards
+    nb = 512                                              # 2048 texels = 512 blocks per edge
+    nblk = nb * nb
+    mine = plan_shards([1.0] * total_images, world)[rank]
+    ua = [i for i in mine if i % 2 == 0]
+    es = [i for i in mine if i % 2 == 1]
+    res = {"workload": "%d textures of 2048x2048 (even = UASTC, odd = ETC1S), image i on rank i mod %d" % (total_images, world),
+           "images_this_rank": len(mine)}
+    # ---- UASTC share: distinct device buffers per image, seeded by the image index ----
+    t_rgba = t_bc7 = 0.0
+    if ua:
+        d_in = [torch.from_numpy(make_payload(payload, nblk, seed=1000 + i).reshape(-1)).cuda() for i in ua]
+        o_rgba = [torch.empty(nblk * 64, dtype=torch.uint8, device="cuda") for _ in range(min(len(ua), 8))]
+        o_bc7 = [torch.empty(nblk * 16, dtype=torch.uint8, device="cuda") for _ in range(min(len(ua), 8))]
+        for tgt, outs, ob in ((0, o_rgba, 64), (2, o_bc7, 16)):
+            for rep in range(2):
+                a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for k in range(len(ua)):
+                    assert L.b2bu_uastc_transcode_dev(tgt, d_in[k].data_ptr(), nblk * 16, nb, outs[k % len(outs)].data_ptr(), nblk * ob,
+                                                      status.data_ptr(), sh) == 0
+                c.record()
+                torch.cuda.synchronize()
+            if tgt == 0:
+                t_rgba = a.elapsed_time(c) * 1e-3
+            else:
+                t_bc7 = a.elapsed_time(c) * 1e-3
+        del d_in, o_rgba, o_bc7
+    # ---- ETC1S share: one encoded 512x512-block slice per image (same codebooks), all slices of the rank in one call ----
+    t_etc = 0.0
+    if es:
+        orc = ec.bind(load_oracle())
+        n_cb = 2048
+        ep_cb, sel_cb = make_codebooks(n_cb, n_cb, seed=9)
+        ei, si = make_indices(nb, nb, 1, n_cb, n_cb, seed=10)
+        enc = encode(orc, ep_cb, sel_cb, ei, si, nb, nb, 64, False, False)
+        one = ec.slice_bytes(enc, 0)
+        pad = (-len(one)) % 16
+        data = (one + b"\0" * pad) * len(es)
+        ofs = (ctypes.c_uint64 * len(es))(*[i * (len(one) + pad) for i in range(len(es))])
+        lens = (ctypes.c_uint64 * len(es))(*[len(one)] * len(es))
+        dec = b.Etc1sDecoder(n_cb, n_cb, enc["endpoints"], enc["selectors"], enc["tables"])
+        out = torch.empty(nblk * 64 * len(es), dtype=torch.uint8).pin_memory()
+        buf = ctypes.create_string_buffer(data, len(data))
+        for rep in range(2):
+            assert L.b2bu_etc1s_transcode_slices(dec._h, 0, nb, nb, buf, len(data), ofs, lens, len(es), out.data_ptr(), out.numel()) == 0
+        k2, k3 = ctypes.c_float(), ctypes.c_float()
+        L.b2bu_etc1s_last_timing(dec._h, ctypes.byref(k2), ctypes.byref(k3), None, None)
+        t_etc = (k2.value + k3.value) * 1e-3
+        res["etc1s_entropy_ms"] = k2.value
+        res["etc1s_gather_ms"] = k3.value
+        dec.close()
+        del out
+    times = torch.tensor([t_rgba, t_bc7, t_etc, t_rgba + t_etc], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([len(ua), len(es)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)      # timing only: max over ranks
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    tr, tb, te, tm = [float(x) for x in times.tolist()]
+    nu, ne = [float(x) for x in counts.tolist()]
+    tex = nblk * 16
+    res.update({"uastc_to_rgba_gtexel_s": nu * tex / tr / 1e9 if tr else None, "uastc_to_bc7_gtexel_s": nu * tex / tb / 1e9 if tb else None,
+                "etc1s_to_rgba_device_gtexel_s": ne * tex / te / 1e9 if te else None,
+                "mixed_to_rgba_device_gtexel_s": (nu + ne) * tex / tm / 1e9 if tm else None, "n_gpus": world})
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--target", default="astc", choices=list(TARGET_NAMES))
@@ -309,8 +384,9 @@ def main():
     ap.add_argument("--cpu-sample-blocks", type=int, default=1 << 20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--all-targets", action="store_true", help="also report the other targets / payloads in 'extra'")
-    ap.add_argument("--configs", default="c3,c4", help="extra BASELINE configs measured on rank 0 and reported under 'configs' (c3 = BC7 mip chain, "
-                    "c4 = ETC1S slices); '' to skip")
+    ap.add_argument("--c5-images", type=int, default=64, help="images in the mixed batch of configs[4] (BASELINE names 4096)")
+    ap.add_argument("--configs", default="c3,c4,c5", help="extra BASELINE configs measured on rank 0 and reported under 'configs' (c3 = BC7 mip chain, "
+                    "c4 = ETC1S slices, c5 = mixed batch sharded by image over the ranks); 'none' to skip")
     ap.add_argument("--c4-blocks", type=int, default=1024, help="ETC1S slice edge in blocks (1024 = 4096x4096 texels)")
     ap.add_argument("--c4-slices", type=int, default=64)
     args = ap.parse_args()
@@ -456,9 +532,25 @@ def main():
             cfgs["c3_bc7_mip_chain"] = bench_c3_bc7_mips(L, torch, args.payload, 50, status, sh)
         if "c4" in want_cfg:
             cfgs["c4_etc1s"] = bench_c4_etc1s(L, b, args.c4_blocks, args.c4_slices)
+    if args.configs and "c5" in args.configs.split(","):
+        c5 = bench_c5_mixed_batch(L, b, torch, dist, rank, world, args.payload, args.c5_images, status, sh)     # every rank takes part
+        if rank == 0:
+            cfgs["c5_mixed_batch"] = c5
     if world > 1:
         dist.barrier()
 
+    int_bound = None
+    if rank == 0:
+        # secondary bound of north_star's roofline definition: integer ops / INT throughput, with the op count per block
+        # fixed by SURVEY.md section 8d and the INT throughput measured on this device by the library's probe
+        alu, mix = ctypes.c_double(), ctypes.c_double()
+        if L.b2bu_probe_int_peak(ctypes.byref(alu), ctypes.byref(mix)) == 0 and mix.value > 0:
+            ops = INT_OPS[target]
+            t_int = n * ops / (mix.value * 1e12)
+            int_bound = {"alu_pipe_tops": alu.value, "alu_fma_mix_tops": mix.value, "contract_ops_per_block": ops,
+                         "bound_us_at_mix_peak": t_int * 1e6, "frac_of_int_bound": t_int / (ms_per_step * 1e-3),
+                         "note": "SURVEY 8d op counts are estimates of a minimal table-driven formulation; > 1 means the kernel "
+                                 "needs fewer instructions than the estimate and the HBM bound is the binding one"}
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         achieved = n * ALGO_BYTES[target] / (ms_per_step * 1e-3) / 1e9
@@ -475,7 +567,8 @@ def main():
                        "sharding": "one texture per GPU, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.target), "peak_source": peak_src,
-                         "algorithmic_bytes_per_block": ALGO_BYTES[target], "kernel": "uastc_transcode_kernel<%s>" % args.target.upper()},
+                         "algorithmic_bytes_per_block": ALGO_BYTES[target], "kernel": "uastc_sorted_kernel<%s>" % args.target.upper(),
+                         "int_bound": int_bound},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Gtexel/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * ob,
                     "steps": args.e2e_steps, "launches": int(e2e_launches), "api": "b2bu_uastc_transcode (pinned host buffers)"},

@@ -104,6 +104,10 @@ int b2bu_uastc_transcode_dev(int target, const void* d_blocks, size_t nbytes, si
                              size_t out_bytes, void* d_status, void* stream);
 int b2bu_status_reset_dev(void* d_status, void* stream);
 int b2bu_status_read_dev(const void* d_status, void* stream, uint64_t* first_bad_block);
+/* Measurement aid: thread-level integer instruction throughput of the current device in Tops/s, for a stream of alu-pipe
+ * instructions (LOP3 / SHF) and for an alu / fma-pipe mix (LOP3 / IMAD).  This is the INT denominator of the roofline
+ * (north_star: the slower of bytes / HBM bandwidth and integer ops / INT throughput). */
+int b2bu_probe_int_peak(double* alu_tops, double* mixed_tops);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
 uint64_t b2bu_launch_count(void);
 
