@@ -192,7 +192,7 @@ template <int TARGET> struct PipeCfg {
     static constexpr size_t OUT_SLOT = IN_PLACE ? 0 : (size_t)TILE * OB;
     static constexpr size_t OFF_ORDER = OFF_OUT + 2 * OUT_SLOT;
     static constexpr size_t OFF_INFO = OFF_ORDER + 2 * (size_t)MAXORD * 2;
-    static constexpr size_t OFF_WCNT = (OFF_INFO + 2 * (size_t)MAXITEMS * 2 + 15) / 16 * 16;
+    static constexpr size_t OFF_WCNT = (OFF_INFO + 2 * 32 * 4 + 15) / 16 * 16;
     static constexpr size_t OFF_BASE = OFF_WCNT + (size_t)SORT_WARPS * 32 * 4;
     static constexpr size_t OFF_CTL = OFF_BASE + (size_t)SORT_WARPS * 32 * 4;
     static constexpr size_t OFF_BAR = OFF_CTL + 2 * 4 * 4;
@@ -220,14 +220,20 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
     uint4* in_s = reinterpret_cast<uint4*>(smem + C::OFF_IN);                 // [2][TILE]
     unsigned char* out_s = smem + C::OFF_OUT;                                 // [2][OUT_SLOT]
     uint16_t* order = reinterpret_cast<uint16_t*>(smem + C::OFF_ORDER);       // [2][MAXORD]
-    uint16_t* info = reinterpret_cast<uint16_t*>(smem + C::OFF_INFO);         // [2][MAXITEMS]: mode | lanes << 8
+    uint32_t* bintab = reinterpret_cast<uint32_t*>(smem + C::OFF_INFO);       // [2][32], in bin order: first item | blocks in the bin << 16
     uint32_t* wcnt = reinterpret_cast<uint32_t*>(smem + C::OFF_WCNT);         // [SORT_WARPS][32]
     uint32_t* wbase = reinterpret_cast<uint32_t*>(smem + C::OFF_BASE);        // [SORT_WARPS][32]
     uint32_t* ctl = reinterpret_cast<uint32_t*>(smem + C::OFF_CTL);           // [2][4]: next item, number of items
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);          // full[2], sorted[2], done[2]
     uint64_t* bar_full = bars, *bar_sorted = bars + 2, *bar_done = bars + 4;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // role order by hardware warp id: B2BU_SORT_FIRST = 1 puts the sorter warps at the low ids
+#ifndef B2BU_SORT_FIRST
+#define B2BU_SORT_FIRST 0
+#endif
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int hwarp = tid >> 5;
+    const int warp = B2BU_SORT_FIRST ? (hwarp < C::SORT_WARPS ? hwarp + C::WORK_WARPS : hwarp < C::SORT_WARPS + C::WORK_WARPS ? hwarp - C::SORT_WARPS : hwarp) : hwarp;
 
     // this CTA's contiguous block range, cut into equal tiles of at most TILE blocks (multiples of 32)
     const uint64_t r0 = cta_range_start(nblocks, range_quot, range_rem, blockIdx.x, gridDim.x);
@@ -311,7 +317,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
 
     if (warp >= C::WORK_WARPS) {
         // ================================ sorter warps ================================
-        const int sw = warp - C::WORK_WARPS, st = tid - 32 * C::WORK_WARPS;
+        const int sw = warp - C::WORK_WARPS, st = sw * 32 + lane;
         uint32_t* mycnt = wcnt + sw * 32;
         for (uint32_t k = 0; k < ntiles; k++) {
             const uint32_t s = k & 1u, u = k >> 1, nt = tile_blocks(k);
@@ -357,31 +363,28 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
             PH(2);
             named_bar_sync(1, C::SORT_THREADS);
             PH(3);
-            // B: bin offsets (each bin padded to a multiple of 32, heaviest mode first), item table
-            if (sw == 0) {
+            // B: bin offsets (each bin padded to a multiple of 32, heaviest mode first).  Every sorter warp computes the
+            // scan redundantly from the warp counters (no hand-off, no second barrier); lane l owns bin kBinOrder[l].
+            {
                 const uint32_t bin = lane < kBins ? (uint32_t)kBinOrder[lane] : 31u;
-                uint32_t cw[C::SORT_WARPS], c = 0;
+                uint32_t cw[C::SORT_WARPS], c = 0, mine_base = 0;
 #pragma unroll
                 for (int w = 0; w < C::SORT_WARPS; w++) cw[w] = wcnt[w * 32 + bin];
 #pragma unroll
-                for (int w = 0; w < C::SORT_WARPS; w++) { const uint32_t v = lane < kBins ? cw[w] : 0u; cw[w] = c; c += v; }
+                for (int w = 0; w < C::SORT_WARPS; w++) { if (w == sw) mine_base = c; c += lane < kBins ? cw[w] : 0u; }
                 const uint32_t padded = (c + 31u) & ~31u;
                 uint32_t incl = padded;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += v; }
                 const uint32_t excl = incl - padded;
-                if (lane < kBins) {
-#pragma unroll
-                    for (int w = 0; w < C::SORT_WARPS; w++) wbase[w * 32 + bin] = cw[w] + excl;
-                    for (uint32_t j = 0; j < (padded >> 5); j++) {
-                        const uint32_t lanes = c - 32u * j < 32u ? c - 32u * j : 32u;
-                        info[s * C::MAXITEMS + (excl >> 5) + j] = (uint16_t)(bin | (lanes << 8));
-                    }
+                wbase[sw * 32 + bin] = mine_base + excl;                        // this warp's first slot in each bin (bin 31 is a dummy)
+                if (sw == 0) {
+                    bintab[s * 32 + lane] = (excl >> 5) | (c << 16);             // workers: item -> (mode, lanes) without a per-item table
+                    if (lane == 31) { ctl[s * 4 + 0] = 0; ctl[s * 4 + 1] = incl >> 5; }
                 }
-                if (lane == 31) { ctl[s * 4 + 0] = 0; ctl[s * 4 + 1] = incl >> 5; }
             }
             PH(4);
-            named_bar_sync(1, C::SORT_THREADS);
+            __syncwarp();
             PH(5);
             // C: scatter block indices into their bins
             const uint32_t* mybase = wbase + sw * 32;
@@ -408,7 +411,6 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
         uint4* tin = in_s + s * C::TILE;
         unsigned char* tout = out_s + s * C::OUT_SLOT;
         const uint16_t* ord = order + s * C::MAXORD;
-        const uint16_t* inf = info + s * C::MAXITEMS;
         const uint64_t base = r0 + tile_start(k);
 #ifdef B2BU_TRACE
         const long long tw0 = clock64();
@@ -419,6 +421,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
 #endif
         mbar_wait(&bar_full[s], u & 1u);          // completed long ago: observes the bulk-copied bytes directly
         const uint32_t nitems = ctl[s * 4 + 1];
+        const uint32_t bt = bintab[s * 32 + lane];
         // Items are pulled in bin order from a shared counter.  Besides balancing uneven items this keeps every worker of
         // the SM inside the same few modes, i.e. the same few KB of code: dealing the items round-robin instead let the
         // warps drift apart and ran the large-code targets (ETC1/ETC2) 3x slower on instruction-cache misses.  ASTC's
@@ -430,9 +433,12 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
                 item = __shfl_sync(0xFFFFFFFFu, item, 0);
             }
             if (item >= nitems) break;
-            const uint32_t inf_w = inf[item];
-            const uint32_t mode = inf_w & 0xFFu;
-            if ((uint32_t)lane < (inf_w >> 8)) {
+            // bin of this item: lanes hold the bins' first items in bin order (non-decreasing; empty bins repeat the value)
+            const uint32_t nle = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, lane < kBins && (bt & 0xFFFFu) <= item));
+            const uint32_t bsel = __shfl_sync(0xFFFFFFFFu, bt, (int)nle - 1);
+            const uint32_t mode = kBinOrder[nle - 1u];
+            const uint32_t rest = (bsel >> 16) - 32u * (item - (bsel & 0xFFFFu));      // blocks of the bin from this item on
+            if ((uint32_t)lane < rest) {
                 const uint32_t idx = ord[item * 32 + lane];
                 const uint4 b = tin[idx];
                 BlockOut o;
