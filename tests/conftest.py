@@ -31,13 +31,13 @@ def build_oracle() -> pathlib.Path:
     return so
 
 
-def build_emu() -> pathlib.Path:
-    so = ROOT / "tests" / "emu" / "libemu_uastc.so"
+def build_emu(palette: bool = False) -> pathlib.Path:
+    so = ROOT / "tests" / "emu" / ("libemu_uastc_pal.so" if palette else "libemu_uastc.so")
     csrc = ROOT / "basisu_rs_b200" / "csrc"
     deps = [ROOT / "tests" / "emu" / "emu_uastc.cpp", csrc / "uastc_device.cuh", csrc / "device_tables.h", csrc / "device_tables_gen.inc"]
     if _newer(so, deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fvisibility=hidden",
-                        "-Wno-attributes", "-o", str(so), str(deps[0])], check=True)
+                        "-Wno-attributes", "-DB2BU_PALETTE=%d" % int(palette), "-o", str(so), str(deps[0])], check=True)
     return so
 
 
@@ -54,6 +54,15 @@ def oracle():
     L.orc_bitwriter_msb.argtypes = [c.c_void_p, c.c_size_t, c.c_size_t, c.c_uint, c.c_uint32, c.c_int]
     L.orc_unquant_endpoint.restype = c.c_uint8
     L.orc_unquant_endpoint.argtypes = [c.c_uint, c.c_uint, c.c_uint]
+    return L
+
+
+@pytest.fixture(scope="session")
+def emu_palette():
+    """kernel source built with the optional palette path of the RGBA decode switched on (-DB2BU_PALETTE=1)"""
+    L = ctypes.CDLL(str(build_emu(palette=True)))
+    L.emu_uastc_transcode.restype = ctypes.c_uint64
+    L.emu_uastc_transcode.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]
     return L
 
 

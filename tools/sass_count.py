@@ -13,7 +13,7 @@ for m in modes:
         body = "o.v = %s_block<%d>(b, T, pat, cs);" % (tgt, m)
         store = "out[i] = o.v;"
     else:
-        body = "Canon c; canon_front<%d>(b, T, pat, cs, c); out[i] = make_uint4(c.lo_rb[0] ^ c.lo_rb[1] ^ c.lo_rb[2], c.hi_rb[0]^c.hi_rb[1]^c.hi_rb[2]^c.lo_ga[0]^c.lo_ga[1]^c.lo_ga[2]^c.hi_ga[0]^c.hi_ga[1]^c.hi_ga[2], c.w0.x^c.w0.y^c.w0.z^c.w0.w^c.pw, c.w1.x^c.w1.y^c.w1.z^c.w1.w^c.mrb^c.mga);"
+        body = "Canon c; canon_front<" + str(m) + ">(b, T, pat, cs, c); out[i] = make_uint4(c.lo_rb[0] ^ c.lo_rb[1] ^ c.lo_rb[2], c.hi_rb[0]^c.hi_rb[1]^c.hi_rb[2]^c.lo_ga[0]^c.lo_ga[1]^c.lo_ga[2]^c.hi_ga[0]^c.hi_ga[1]^c.hi_ga[2], c.w0.x^c.w0.y^c.w0.z^c.w0.w^c.pw, c.w1.x^c.w1.y^c.w1.z^c.w1.w^c.mrb^c.mga);"
         store = ""
     src.append("extern \"C\" __global__ void k_m%d(const uint4* in, uint4* out) { __shared__ DevTables T; if (threadIdx.x == 0) T = g_t; __syncthreads(); int i = threadIdx.x; uint4 b = in[i]; BlockOut o; uint32_t pat, cs; if (!header_ok<%d>(b, pat, cs)) return; %s %s }\n" % (m, m, body, store))
 if tgt == "rgba":
