@@ -5,6 +5,8 @@
 
 namespace b2bu {
 
+constexpr uint32_t kL1Special = 32u;
+
 enum { ETC1S_OK = 0, ETC1S_ERR_HUFFMAN = 4, ETC1S_ERR_PREDICTION = 6, ETC1S_ERR_VLC = 7, ETC1S_ERR_RANGE = 8 };   // == b2bu_status
 
 struct Etc1sSliceJob {
@@ -21,14 +23,15 @@ struct Etc1sDecodeParams {
     uint32_t num_slices;
     uint32_t* out_idx;              // per block: endpoint_index | selector_index << 16
     uint8_t* scratch;
-    const uint32_t* l1;             // 4 first-level tables of 1024 entries: symbol << 5 | code size (0 = no code, ~0 = long code)
-    const uint32_t* flat[4];        // full flat tables (huffman.rs:151), same entry format, 1 << max_len entries
+    // four first-level tables back to back (copied to shared memory): table t has 1 << l1_bits[t] entries starting at word
+    // l1_ofs[t] (l1_ofs[4] = total words).  Entry = symbol << 8 | special << 5 | code size; `special` (kL1Special) marks
+    // everything the fast path does not handle: codes longer than l1_bits (size 0 -> look in `flat`), slots without a
+    // code, and the run symbols (endpoint-pred repeat 256, selector-history RLE).
+    const uint32_t* l1;
+    uint32_t l1_bits[4];
+    uint32_t l1_ofs[5];
+    const uint32_t* flat[4];        // full flat tables (huffman.rs:151): symbol << 5 | code size, 1 << max_len entries
     uint32_t max_len[4];
-    // long codes (> 10 bits): canonical description per table, 16 x upper then 16 x base (see HuffModel), and the sorted symbols
-    const uint32_t* canon;
-    const uint16_t* syms;
-    uint32_t sym_ofs[5];
-    uint32_t canon_ok;              // bit t set: table t is a valid prefix code and `canon` applies; else the flat table is read
     uint32_t num_endpoints, num_selectors, hist_size, is_video;
     uint32_t* status;               // per slice: 0 or an ETC1S_ERR_* code
 };
@@ -39,7 +42,8 @@ __host__ __device__ inline uint64_t etc1s_row_state_bytes(uint32_t nbx)
     return (((uint64_t)nbx + 7u) & ~7ull) * 2u + ((((uint64_t)nbx + 1u) / 2u + 15u) & ~15ull);
 }
 
-cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, int warps_per_cta, uint32_t max_nbx, cudaStream_t stream);
+// slices_per_cta: slice pipelines (one tokenizer warp + one resolver warp each) per CTA; 0 = choose from the slice count
+cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, int slices_per_cta, uint32_t max_nbx, int sm_count, cudaStream_t stream);
 cudaError_t launch_etc1s_gather_etc1(const uint32_t* idx, uint64_t nblocks, const uint32_t* endpoints, const uint32_t* sel_etc1, void* out,
                                      int sm_count, cudaStream_t stream);
 cudaError_t launch_etc1s_gather_rgba(const uint32_t* idx_rgb, const uint32_t* idx_alpha, uint32_t nbx, uint64_t nblocks, const uint32_t* endpoints,

@@ -19,6 +19,9 @@ namespace b2bu {
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
 
+// shared memory given to the four first-level Huffman tables of K2 (the rest holds the per-slice pipelines)
+constexpr size_t kL1BudgetBytes = 128 * 1024;
+
 // ---- bit cursor: LSB first, bytes past the end read as zero (src/bitreader.rs:27-60) ----------
 struct BitCursor {
     const uint8_t* p; size_t len; uint64_t pos = 0;
@@ -38,13 +41,7 @@ struct BitCursor {
 struct HuffModel {
     std::vector<uint32_t> flat;     // 1 << max_len entries of symbol << 5 | code size (0 = no code), as huffman.rs:151-170 fills them
     unsigned max_len = 0;
-    // canonical form for the kernel's long-code path (valid prefix codes only, else canon_ok = false and the kernel reads `flat`):
-    // a 16-bit MSB-first window v has a code of length l iff v < upper[l-1] and v >= upper[l-2]; its symbol is
-    // syms[base[l-1] + (v >> (16 - l))]
-    bool canon_ok = false;
-    uint32_t upper[16] = {0};
-    int32_t base[16] = {0};
-    std::vector<uint16_t> syms;     // symbols sorted by (code length, symbol)
+    uint32_t count[17] = {0};       // codes per length (count[0] unused)
 };
 
 static uint32_t bit_reverse32(uint32_t x)
@@ -85,24 +82,7 @@ static int huff_from_sizes(const std::vector<uint8_t>& sizes, HuffModel& m)
         next[size]++;
     }
     for (unsigned b = 0; b <= 16; b++) if (next[b] > 65536u) return B2BU_ERR_HUFFMAN;   // "codes don't fit into 16 bits"
-    // canonical description (only meaningful for a prefix-free set: Kraft sum <= 1)
-    uint64_t kraft = 0;
-    for (unsigned b = 1; b <= 16; b++) kraft += (uint64_t)count[b] << (16 - b);
-    m.canon_ok = kraft <= 65536u && sizes.size() <= 65536u;
-    if (m.canon_ok) {
-        uint32_t first = 0, ofs = 0, offset[17] = {0};
-        for (unsigned b = 1; b <= 16; b++) {
-            first = (first + count[b - 1]) << 1;
-            offset[b] = ofs;
-            m.upper[b - 1] = (first + count[b]) << (16 - b);
-            m.base[b - 1] = (int32_t)ofs - (int32_t)first;
-            ofs += count[b];
-        }
-        m.syms.assign(ofs, 0);
-        uint32_t fill[17];
-        for (unsigned b = 0; b <= 16; b++) fill[b] = offset[b];
-        for (size_t sym = 0; sym < sizes.size(); sym++) if (sizes[sym]) m.syms[fill[sizes[sym]]++] = (uint16_t)sym;
-    }
+    for (unsigned b = 1; b <= 16; b++) m.count[b] = count[b];
     return B2BU_OK;
 }
 
@@ -145,17 +125,47 @@ static int read_huffman_table(BitCursor& c, HuffModel& out)
     return huff_from_sizes(sizes, out);
 }
 
-// first-level table for shared memory: an entry is usable iff every flat slot that shares its low
-// 10 bits holds the same short code; otherwise the kernel falls back to the flat table
-static void build_l1(const HuffModel& m, uint32_t* l1)
+// First-level table of `bits` bits for shared memory (entry format: etc1s_device.h).  A slot is directly usable iff every
+// flat slot that shares its low `bits` bits holds the same code of at most `bits` bits; everything else, and the symbol
+// `run_sym` (a run marker the fast path does not handle), is flagged special.
+static void build_l1(const HuffModel& m, unsigned bits, uint32_t run_sym, uint32_t* l1)
 {
-    const unsigned L = 10;
-    for (uint32_t i = 0; i < (1u << L); i++) {
-        if (m.max_len <= L) { l1[i] = m.flat[i & ((1u << m.max_len) - 1u)]; continue; }
-        const uint32_t first = m.flat[i];
-        bool same = true;
-        for (uint32_t k = 1; k < (1u << (m.max_len - L)) && same; k++) same = m.flat[i | (k << L)] == first;
-        l1[i] = (same && (first & 31u) <= L) ? first : 0xFFFFFFFFu;
+    for (uint32_t i = 0; i < (1u << bits); i++) {
+        uint32_t f;
+        bool ok = true;
+        if (m.max_len <= bits) f = m.flat[i & ((1u << m.max_len) - 1u)];
+        else {
+            f = m.flat[i];
+            for (uint32_t k = 1; k < (1u << (m.max_len - bits)) && ok; k++) ok = m.flat[i | (k << bits)] == f;
+            ok = ok && (f & 31u) <= bits;
+        }
+        if (!ok || (f & 31u) == 0u) { l1[i] = kL1Special; continue; }               // long code or no code: size 0
+        const uint32_t sym = f >> 5;
+        l1[i] = (sym << 8) | (sym == run_sym ? kL1Special : 0u) | (f & 31u);
+    }
+}
+
+// First-level widths for the four slice models under a shared-memory budget: start at <= 10 bits and keep widening the
+// table whose long codes cost most (Kraft mass of the codes that do not fit x how often the model is read per block).
+static void choose_l1_bits(const HuffModel* models, size_t budget_bytes, unsigned* bits)
+{
+    static const double weight[4] = {0.25, 0.5, 1.0, 0.02};     // predictor symbol per 2x2 group, delta, selector, run length
+    auto mass = [&](int t, unsigned L) { double s = 0; for (unsigned b = L + 1; b <= 16; b++) s += models[t].count[b] / double(1u << b); return s * weight[t]; };
+    size_t used = 0;
+    for (int t = 0; t < 4; t++) { bits[t] = std::min(models[t].max_len, 10u); used += (size_t)4 << bits[t]; }
+    for (;;) {
+        // widen the table with the largest remaining cost (not the largest marginal gain: a table whose codes are all
+        // 12 bits long gains nothing from the step 10 -> 11)
+        int best = -1;
+        double best_cost = 0;
+        for (int t = 0; t < 4; t++) {
+            if (bits[t] >= models[t].max_len || bits[t] >= 15u || used + ((size_t)4 << bits[t]) > budget_bytes) continue;
+            const double cost = mass(t, bits[t]);
+            if (cost > best_cost) { best = t; best_cost = cost; }
+        }
+        if (best < 0) break;
+        used += (size_t)4 << bits[best];
+        bits[best]++;
     }
 }
 
@@ -172,12 +182,9 @@ struct b2bu_etc1s {
     uint32_t* d_endpoints = nullptr;     // inten | r5 << 8 | g5 << 16 | b5 << 24
     uint32_t* d_sel_plain = nullptr;     // 4 rows, 2 bits per x          (etc.rs:343-361)
     uint32_t* d_sel_etc1 = nullptr;      // ETC1 bit planes               (etc.rs:363-393)
-    uint32_t* d_l1 = nullptr;            // 4 x 1024
+    uint32_t* d_l1 = nullptr;            // the four first-level tables back to back
+    uint32_t l1_bits[4] = {0, 0, 0, 0}, l1_ofs[5] = {0, 0, 0, 0, 0};
     uint32_t* d_flat[4] = {nullptr, nullptr, nullptr, nullptr};
-    uint32_t* d_canon = nullptr;         // 4 x {16 upper, 16 base}
-    uint16_t* d_syms = nullptr;          // the four sorted symbol arrays back to back
-    uint32_t sym_ofs[5] = {0, 0, 0, 0, 0};
-    uint32_t canon_ok = 0;               // bit t: table t has a canonical description
     // per-call scratch (grow only)
     void* d_data = nullptr; size_t data_cap = 0;
     void* d_idx = nullptr; size_t idx_cap = 0;
@@ -262,14 +269,11 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
     P.out_idx = static_cast<uint32_t*>(h->d_idx);
     P.scratch = static_cast<uint8_t*>(h->d_scratch);
     P.l1 = h->d_l1;
-    for (int t = 0; t < 4; t++) { P.flat[t] = h->d_flat[t]; P.max_len[t] = h->max_len[t]; P.sym_ofs[t] = h->sym_ofs[t]; }
-    P.sym_ofs[4] = h->sym_ofs[4]; P.canon = h->d_canon; P.syms = h->d_syms; P.canon_ok = h->canon_ok;
+    for (int t = 0; t < 4; t++) { P.flat[t] = h->d_flat[t]; P.max_len[t] = h->max_len[t]; P.l1_bits[t] = h->l1_bits[t]; P.l1_ofs[t] = h->l1_ofs[t]; }
+    P.l1_ofs[4] = h->l1_ofs[4];
     P.num_endpoints = h->num_endpoints; P.num_selectors = h->num_selectors; P.hist_size = h->hist_size; P.is_video = h->is_video ? 1u : 0u;
     P.status = static_cast<uint32_t*>(h->d_status);
-    // one warp per slice; spread slices over SMs first, pack warps (which share the tables in shared memory) when there are many slices:
-    // a lone warp issues one dependent instruction every ~6 cycles, 16 warps per SM keep the issue slots busy
-    const int warps = ns >= (size_t)c->sm_count * 16 ? 16 : ns >= (size_t)c->sm_count * 4 ? 4 : 1;
-    CK(launch_etc1s_decode(P, warps, max_nbx, s));
+    CK(launch_etc1s_decode(P, 0, max_nbx, c->sm_count, s));
     count_launch(1);
     CK(cudaEventRecord(h->ev[1], s));
 
@@ -365,29 +369,21 @@ static int etc1s_open_impl(uint32_t endpoint_count, uint32_t selector_count, con
         for (int t = 0; t < 4; t++) if ((st = read_huffman_table(bc, models[t]))) return st;
         h->hist_size = bc.read(13);
     }
-    std::vector<uint32_t> l1(4 * 1024);
-    for (int t = 0; t < 4; t++) { build_l1(models[t], l1.data() + t * 1024); h->max_len[t] = models[t].max_len; }
+    unsigned bits[4];
+    choose_l1_bits(models, kL1BudgetBytes, bits);
+    std::vector<uint32_t> l1;
+    const uint32_t run_sym[4] = {256u, 0xFFFFFFFFu, (h->hist_size + selector_count) & 0xFFFFu, 0xFFFFFFFFu};   // mod.rs:220-222
+    for (int t = 0; t < 4; t++) {
+        h->l1_bits[t] = bits[t]; h->l1_ofs[t] = (uint32_t)l1.size(); h->max_len[t] = models[t].max_len;
+        l1.resize(l1.size() + ((size_t)1 << bits[t]));
+        build_l1(models[t], bits[t], run_sym[t], l1.data() + h->l1_ofs[t]);
+    }
+    h->l1_ofs[4] = (uint32_t)l1.size();
 
     CK(cudaSetDevice(h->device));
     if ((st = upload(&h->d_endpoints, endpoints)) || (st = upload(&h->d_sel_plain, sel_plain)) || (st = upload(&h->d_sel_etc1, sel_etc1)) ||
         (st = upload(&h->d_l1, l1))) return st;
     for (int t = 0; t < 4; t++) if ((st = upload(&h->d_flat[t], models[t].flat))) return st;
-    {
-        std::vector<uint32_t> canon(4 * 32, 0);
-        std::vector<uint16_t> syms;
-        for (int t = 0; t < 4; t++) {
-            h->sym_ofs[t] = (uint32_t)syms.size();
-            if (!models[t].canon_ok) continue;
-            h->canon_ok |= 1u << t;
-            for (int l = 0; l < 16; l++) { canon[t * 32 + l] = models[t].upper[l]; canon[t * 32 + 16 + l] = (uint32_t)models[t].base[l]; }
-            syms.insert(syms.end(), models[t].syms.begin(), models[t].syms.end());
-        }
-        h->sym_ofs[4] = (uint32_t)syms.size();
-        if ((st = upload(&h->d_canon, canon))) return st;
-        syms.resize((syms.size() + 1) & ~size_t(1), 0);
-        CK(cudaMalloc(&h->d_syms, std::max<size_t>(syms.size(), 2) * 2));
-        if (!syms.empty()) CK(cudaMemcpy(h->d_syms, syms.data(), syms.size() * 2, cudaMemcpyHostToDevice));
-    }
     *out = h.release();
     return B2BU_OK;
 }
@@ -448,7 +444,6 @@ void b2bu_etc1s_close(b2bu_etc1s* h)
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     cudaFree(h->d_endpoints); cudaFree(h->d_sel_plain); cudaFree(h->d_sel_etc1); cudaFree(h->d_l1);
     for (int t = 0; t < 4; t++) cudaFree(h->d_flat[t]);
-    cudaFree(h->d_canon); cudaFree(h->d_syms);
     cudaFree(h->d_data); cudaFree(h->d_idx); cudaFree(h->d_out); cudaFree(h->d_scratch); cudaFree(h->d_jobs); cudaFree(h->d_status);
     delete h;
 }
@@ -461,6 +456,13 @@ int b2bu_etc1s_last_timing(b2bu_etc1s* h, float* entropy_ms, float* gather_ms, f
     if (gather_ms) *gather_ms = h->last_ms[1];
     if (d2h_ms) *d2h_ms = h->last_ms[2];
     if (blocks) *blocks = h->last_blocks;
+    return B2BU_OK;
+}
+
+int b2bu_etc1s_table_info(b2bu_etc1s* h, uint32_t l1_bits[4], uint32_t max_code_len[4])
+{
+    if (!h) return B2BU_ERR_ARGUMENT;
+    for (int t = 0; t < 4; t++) { if (l1_bits) l1_bits[t] = h->l1_bits[t]; if (max_code_len) max_code_len[t] = h->max_len[t]; }
     return B2BU_OK;
 }
 

@@ -1,16 +1,29 @@
 // ETC1S / BasisLZ device side (K2 entropy decode, K3 codebook gather).
 //
-// K2  etc1s_entropy_decode: ONE WARP PER SLICE.  The slice bitstream is an inherently serial chain
-//     (reference src/basis_lz/mod.rs:188-458), so the warp runs the chain redundantly on all lanes
-//     (identical state, broadcast shared-memory reads -- no shuffles on the critical path) and uses
-//     its 32 lanes for everything that is parallel: staging the compressed bytes into a shared
-//     window with coalesced loads, pre-loading the previous row's endpoint indices for the
-//     "up / up-left" predictors, and flushing the decoded (endpoint, selector) pairs coalesced.
-//     The four Huffman models live in shared memory as 10-bit first-level tables; longer codes
-//     fall back to the full flat table (huffman.rs:151) in global memory.
+// K2  etc1s_entropy_decode: the slice bitstream is one serial chain (reference src/basis_lz/mod.rs:188-458),
+//     but only the BIT POSITION is inherently serial: which table is read next depends on the predictor bits
+//     and the two run counters, never on the endpoint values or on the selector history.  So every slice is
+//     decoded by a two-stage pipeline of two warps connected by a token ring in shared memory:
+//
+//       tokenizer warp   walks the bitstream and emits one token per block: predictor (2 bits), the endpoint
+//                        delta symbol, the raw selector symbol (codebook index, history reference or run
+//                        repeat).  Its dependent chain per symbol is  AND -> LDS (first-level table in shared
+//                        memory, up to 15 bits wide) -> funnel shift;  the 32-bit refill, the run counters and
+//                        the token stores are off that chain.  All lanes run the chain redundantly on
+//                        identical state (broadcast shared reads); the lanes are used for the parallel parts:
+//                        staging the compressed bytes into a shared ring with coalesced 16-byte loads.
+//       resolver warp    turns 32 tokens at a time into (endpoint, selector) pairs: the endpoint predictors
+//                        (left / up / up-left / delta) are a segmented scan over the warp (composition of
+//                        "set to c" and "add d mod n"), the approximate-move-to-front selector history is the
+//                        one remaining serial loop (a shared-memory load and two stores per history hit); then
+//                        one coalesced store of the 32 index words and the row state for the next row.
+//
+//     Errors keep the reference's order: every check has a key (block, phase) and the slice status is the code
+//     of the smallest key over both warps.
 // K3  etc1s_gather_etc1 / etc1s_gather_rgba: one thread per block, pure gather
 //     (mod.rs:122-146, :163-181).
 #include "etc1s_device.h"
+#include "ptx_helpers.cuh"
 
 namespace b2bu {
 
@@ -18,89 +31,96 @@ namespace b2bu {
 __device__ const int16_t kEtc1Mod[32] = {-8, -2, 2, 8, -17, -5, 5, 17, -29, -9, 9, 29, -42, -13, 13, 42,
                                         -60, -18, 18, 60, -80, -24, 24, 80, -106, -33, 33, 106, -183, -47, 47, 183};
 
-constexpr int kL1Bits = 10;
-constexpr int kL1Size = 1 << kL1Bits;
-constexpr uint32_t kLong = 0xFFFFFFFFu;          // first-level entry: code longer than kL1Bits
-constexpr int kRound = 32;                        // blocks decoded between two cooperative phases
+constexpr int kRound = 32;                        // blocks per token round
+constexpr int kTokRounds = 4;                     // depth of the token ring
 constexpr int kHalfBytes = 1024;                  // the compressed-byte ring is refilled in 1 KiB pieces
-constexpr int kRingHalves = 4;                    // 4 KiB ring per warp: the piece being read, the next, one in flight
+constexpr int kRingHalves = 4;                    // 4 KiB ring per slice: the piece being read, the next, one in flight
 constexpr int kRingWords = kRingHalves * kHalfBytes / 4;
 // A round of 32 blocks consumes well under one piece: per block at most one predictor symbol (16 bits) with
 // a 4-bit-chunk VLC (40), a delta (16), a selector symbol (16), a run symbol (16) and a 7-bit-chunk VLC (40).
 static_assert(kRound * 144 / 8 <= kHalfBytes, "ring piece too small for one round");
 
-struct WarpShared {
-    uint32_t ring[kRingWords];
+// token word A: selector symbol | predictor << 16 | flags; word B: endpoint delta symbol
+constexpr uint32_t kTokSkipSel = 1u << 18;        // texture video, predictor 2: no selector symbol (mod.rs:366)
+constexpr uint32_t kTokErr = 1u << 31;            // tokenizer stopped here: code in bits 24-27, phase in bits 28-30
+// order of the checks inside one block (mod.rs:245-455): predictor symbol (1), predictor asserts (2), delta symbol (3),
+// selector symbols (4), history asserts (5), final range asserts (6)
+enum { PH_PRED_SYM = 1, PH_PRED_CHECK = 2, PH_DELTA = 3, PH_SELECTOR = 4, PH_HISTORY = 5, PH_RANGE = 6 };
+
+struct PipeShared {
+    uint32_t ring[kRingWords];                    // compressed bytes of the slice (tokenizer)
+    uint2 tok[kTokRounds][kRound];                // tokenizer -> resolver
     uint16_t hist[64];                            // selector history when it fits (it always does for real files)
+    uint64_t bar_full[kTokRounds], bar_empty[kTokRounds];
+    uint32_t abort, pad;                          // set by the resolver when it has found an error
 };
 
-struct BitState { uint64_t buf; int avail; uint32_t nextw; };                     // nextw: absolute word index in the slice
+// 64 buffered stream bits (hi:lo, `avail` valid, zeros above), the next ring word already loaded, and `pre`: the low
+// word as it was before the last refill.  Reads take at most 16 bits and every read is followed by a refill to >= 32
+// bits, so `pre` always holds >= 16 valid bits and the next table index can be formed from it without waiting for the
+// refill (which then sits beside the dependent chain, not on it).
+struct BitState { uint32_t lo, hi, pre; int avail; uint32_t nw, nextw; };       // nextw: absolute word index in the slice
 
-__device__ __forceinline__ void bits_ensure32(BitState& s, const uint32_t* ring)
+// Drops e & 31 (<= 16) bits and refills.  Written as predicated PTX so that the refill is straight-line code (the
+// compiler's version of the same C++ is a branch with a convergence barrier around it on every symbol).
+__device__ __forceinline__ void bits_consume(BitState& s, uint32_t e, uint32_t ring_base)      // ring_base: shared address of the ring
 {
-    if (s.avail < 32) {
-        s.buf |= (uint64_t)ring[s.nextw & (kRingWords - 1)] << s.avail;
-        s.avail += 32;
-        s.nextw++;
-    }
-}
-__device__ __forceinline__ void bits_skip(BitState& s, uint32_t n) { s.buf >>= n; s.avail -= (int)n; }
-
-// One Huffman model as the warp sees it: 10-bit first-level table in shared memory for the short codes; longer
-// codes are resolved by a warp-parallel canonical decode (lane l tests code length l+1 against its `upper`
-// bound, a ballot picks the length, a shuffle fetches the symbol index) so that no code needs a global-memory
-// round trip on the serial chain.  `flat` is only read for tables that are not valid prefix codes.
-struct HuffView {
-    const uint32_t* l1;            // shared
-    const uint16_t* syms;          // shared (or global when the symbol arrays do not fit)
-    const uint32_t* flat;          // global
-    uint32_t upper;                // this lane's length bound
-    int32_t base;
-    uint32_t max_len;
-    bool canon;
-};
-
-// huffman.rs:186-198 decode_symbol.  Returns the symbol or 0xFFFFFFFF when no code matches.
-__device__ __forceinline__ uint32_t huff_decode(BitState& s, const uint32_t* ring, const HuffView& h, int lane)
-{
-    bits_ensure32(s, ring);
-    const uint32_t e = h.l1[(uint32_t)s.buf & (kL1Size - 1)];
-    if (e != kLong) {
-        const uint32_t len = e & 31u;
-        if (len == 0u) return 0xFFFFFFFFu;
-        bits_skip(s, len);
-        return e >> 5;
-    }
-    if (h.canon) {
-        const uint32_t v = __brev((uint32_t)s.buf) >> 16;                          // next 16 stream bits, first bit most significant
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, v < h.upper) & 0xFFFFu;
-        if (bal == 0u) return 0xFFFFFFFFu;
-        const uint32_t len = (uint32_t)__ffs((int)bal);                            // 1..16
-        const uint32_t idx = __shfl_sync(0xFFFFFFFFu, (uint32_t)(h.base + (int32_t)(v >> (15 - (lane & 15)))), (int)len - 1);
-        bits_skip(s, len);
-        return h.syms[idx];
-    }
-    const uint32_t f = __ldg(h.flat + ((uint32_t)s.buf & ((1u << h.max_len) - 1u)));
-    const uint32_t len = f & 31u;
-    if (len == 0u) return 0xFFFFFFFFu;
-    bits_skip(s, len);
-    return f >> 5;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 len, sh, a;\n"
+        "shf.r.wrap.b32 %0, %0, %1, %6;\n"                   // lo = (hi:lo) >> len
+        "shf.r.wrap.b32 %1, %1, 0, %6;\n"                    // hi >>= len
+        "and.b32 len, %6, 31;\n"
+        "sub.s32 %3, %3, len;\n"
+        "mov.b32 %2, %0;\n"                                  // pre = lo
+        "setp.lt.s32 p, %3, 32;\n"                           // avail is in [16, 31] when the refill happens
+        "shl.b32 sh, %4, %3;\n"
+        "@p or.b32 %0, %0, sh;\n"
+        "sub.s32 a, 32, %3;\n"
+        "@p shr.u32 %1, %4, a;\n"
+        "@p add.s32 %3, %3, 32;\n"
+        "and.b32 a, %5, %8;\n"
+        "shl.b32 a, a, 2;\n"
+        "add.u32 a, a, %7;\n"
+        "@p ld.shared.u32 %4, [a];\n"
+        "@p add.u32 %5, %5, 1;\n"
+        "}\n"
+        : "+r"(s.lo), "+r"(s.hi), "=r"(s.pre), "+r"(s.avail), "+r"(s.nw), "+r"(s.nextw)
+        : "r"(e), "r"(ring_base), "n"(kRingWords - 1)
+        : "memory");
 }
 
-// mod.rs:585-608 decode_vlc.  Returns false when the reference would panic (ofs >= 32).
-__device__ __forceinline__ bool vlc_decode(BitState& s, const uint32_t* ring, uint32_t chunk_bits, uint32_t& v)
+// Out-of-line slow paths (by value: the bit state must stay in registers on the fast path).
+struct SlowSym { BitState bs; uint32_t sym; };
+// huffman.rs:186-198 for a first-level entry flagged `special`: a run symbol (already consumed) or a code longer than the
+// first-level table, which is looked up in the reference's flat table in global memory.  sym = 0xFFFFFFFF: no code matches.
+__device__ __noinline__ SlowSym huff_slow(BitState bs, uint32_t ring_base, uint32_t e, const uint32_t* __restrict__ flat, uint32_t max_len)
 {
-    v = 0;
-    uint32_t ofs = 0;
+    SlowSym r;
+    if ((e & 31u) != 0u) { r.bs = bs; r.sym = e >> 8; return r; }
+    const uint32_t f = __ldg(flat + (bs.lo & ((1u << max_len) - 1u)));
+    if ((f & 31u) == 0u) { r.bs = bs; r.sym = 0xFFFFFFFFu; return r; }
+    bits_consume(bs, f, ring_base);
+    r.bs = bs; r.sym = f >> 5;
+    return r;
+}
+
+// mod.rs:585-608 decode_vlc.  sym = the value, or 0xFFFFFFFF when the reference would panic (ofs >= 32).
+__device__ __noinline__ SlowSym vlc_decode(BitState bs, uint32_t ring_base, uint32_t chunk_bits)
+{
+    SlowSym r;
+    uint32_t v = 0, ofs = 0;
     for (;;) {
-        bits_ensure32(s, ring);
-        const uint32_t c = (uint32_t)s.buf & ((2u << chunk_bits) - 1u);
-        bits_skip(s, chunk_bits + 1);
+        const uint32_t c = bs.lo & ((2u << chunk_bits) - 1u);
+        bits_consume(bs, chunk_bits + 1u, ring_base);
         v |= (c & ((1u << chunk_bits) - 1u)) << ofs;
         ofs += chunk_bits;
-        if ((c >> chunk_bits) == 0u) return true;
-        if (ofs >= 32u) return false;
+        if ((c >> chunk_bits) == 0u) break;
+        if (ofs >= 32u) { r.bs = bs; r.sym = 0xFFFFFFFFu; return r; }
     }
+    r.bs = bs; r.sym = v;
+    return r;
 }
 
 // One 1 KiB piece of the slice's bytes -> two uint4 per lane (zeros past the end: bitreader.rs:44,55).
@@ -124,160 +144,436 @@ __device__ __forceinline__ void piece_store(uint32_t* ring, uint32_t piece, int 
     dst[lane + 32] = r[1];
 }
 
-// rows_in_smem: the per-slice row state (endpoint indices and predictor bits of the previous row) lives in shared
-// memory when the slice is at most `row_cap` blocks wide, else in the global scratch area (very wide slices).
-__global__ void __launch_bounds__(512) etc1s_entropy_decode_kernel(Etc1sDecodeParams P, uint32_t row_cap, uint32_t sym_smem_bytes)
+#ifdef B2BU_K2_TRACE
+// tuning aid (never in the product build): per-slice cycle / event counters of the two stages
+__device__ unsigned long long g_k2trace[64][8];
+#define K2T(slot, v) do { if (lane == 0 && trace_slice < 64u) g_k2trace[trace_slice][(slot)] += (unsigned long long)(v); } while (0)
+#define K2T_DECL(x) x
+#else
+#define K2T(slot, v) do { } while (0)
+#define K2T_DECL(x)
+#endif
+
+__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+// ---------------------------------------------------------------------------------------------------
+// Stage 1: tokenizer warp.  predrow: one 64-bit word per 32 blocks of the row (2 predictor bits per block), written on
+// even rows for the odd row below (mod.rs:286-296).
+//
+// A lone warp pays the full latency of everything it issues: a shared-memory load and a taken branch cost about the
+// same (~30 cycles), an ALU instruction ~4.  So the hot loop (fast_pair) is straight-line predicated code, two blocks
+// per iteration, with exactly one rarely-taken branch: the table reads a block does not need (no delta symbol, inside
+// a run) are predicated off instead of branched around, and everything unusual (a code longer than the first-level
+// table, a run symbol, an invalid code) only ORs a flag into `spec`; a flagged pair is thrown away and decoded again
+// from the saved state by pair_slow, which follows the reference's control flow literally.
+// ---------------------------------------------------------------------------------------------------
+struct TokState { BitState bs; uint32_t sel_rle, pred_rep, prev_sym, cur, terr; };   // terr: code | phase << 4 when the stream is bad
+
+struct TokConsts {
+    uint32_t t0, t1, t2, t3;          // shared byte addresses of the first-level tables
+    uint32_t m0, m1, m2, m3;          // index masks
+    uint32_t ring_base, num_selectors, rle_sym, is_video;
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* l1s = reinterpret_cast<uint32_t*>(smem_raw);                      // 4 tables x 1024 entries
-    const int nwarps = blockDim.x >> 5;
-    uint16_t* syms_s = reinterpret_cast<uint16_t*>(smem_raw + 4 * kL1Size * sizeof(uint32_t));   // sorted symbols (when they fit)
-    WarpShared* wsh_all = reinterpret_cast<WarpShared*>(smem_raw + 4 * kL1Size * sizeof(uint32_t) + sym_smem_bytes);
-    uint16_t* rows_all = reinterpret_cast<uint16_t*>(wsh_all + nwarps);           // per warp: row_cap endpoint indices + row_cap/2 pred bytes
-    for (int i = threadIdx.x; i < 4 * kL1Size; i += blockDim.x) l1s[i] = P.l1[i];
-    if (sym_smem_bytes) for (uint32_t i = threadIdx.x; i < (P.sym_ofs[4] + 1u) / 2u; i += blockDim.x)
-        reinterpret_cast<uint32_t*>(syms_s)[i] = reinterpret_cast<const uint32_t*>(P.syms)[i];
-    __syncthreads();
+    uint32_t e;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(addr));
+    return e;
+}
+// table read that is skipped (reads as 0: consumes nothing) when `on` is zero
+__device__ __forceinline__ uint32_t lds_u32_if(uint32_t addr, uint32_t on)
+{
+    uint32_t e;
+    asm("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\nmov.u32 %0, 0;\n@p ld.shared.u32 %0, [%1];\n}\n" : "=r"(e) : "r"(addr), "r"(on));
+    return e;
+}
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t slice = blockIdx.x * nwarps + warp;
-    if (slice >= P.num_slices) return;
-    WarpShared& W = wsh_all[warp];
-    const Etc1sSliceJob job = P.jobs[slice];
-    const uint8_t* __restrict__ data = P.data + job.data_ofs;
-    uint32_t* __restrict__ out = P.out_idx + job.out_ofs;
-    const uint32_t nbx = job.nbx, nby = job.nby;
-    const bool rows_in_smem = nbx <= row_cap;
-    // previous row: endpoint index per block (u16) and the predictor bits of every 2x2 group's lower half (u8 per 2 blocks)
-    uint16_t* rowep = rows_in_smem ? rows_all + (size_t)warp * (row_cap + row_cap / 2 + 8)
-                                   : reinterpret_cast<uint16_t*>(P.scratch + job.scratch_ofs);
-    uint8_t* predrow = reinterpret_cast<uint8_t*>(rowep + (rows_in_smem ? row_cap : ((nbx + 7u) & ~7u)));
-    uint16_t* hist = P.hist_size <= 64u ? W.hist : reinterpret_cast<uint16_t*>(P.scratch + job.scratch_ofs + etc1s_row_state_bytes(nbx));
-    const uint32_t num_endpoints = P.num_endpoints, num_selectors = P.num_selectors, hist_size = P.hist_size;
-    const uint32_t rle_sym = (hist_size + num_selectors) & 0xFFFFu;               // mod.rs:220-222 (u16 arithmetic)
-
-    HuffView hv[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        hv[t].l1 = l1s + t * kL1Size;
-        hv[t].syms = (sym_smem_bytes ? syms_s : P.syms) + P.sym_ofs[t];
-        hv[t].flat = P.flat[t];
-        hv[t].upper = P.canon[t * 32 + (lane & 15)];
-        hv[t].base = (int32_t)P.canon[t * 32 + 16 + (lane & 15)];
-        hv[t].max_len = P.max_len[t];
-        hv[t].canon = (P.canon_ok >> t) & 1u;
+// The reference's control flow for one pair of blocks (or the single last block of an odd-width row), mod.rs:259-426.
+// even_row: decode the 2x2 group's predictor symbol (else st.cur already holds the pair's 4 predictor bits).
+__device__ __noinline__ TokState pair_slow(TokState st, const TokConsts K, const Etc1sDecodeParams& P, uint2* tk, uint32_t nblk, uint32_t even_row)
+{
+    BitState bs = st.bs;
+    uint32_t terr = 0, cur = st.cur;
+    if (even_row) {
+        if (st.pred_rep != 0u) { st.pred_rep--; cur = st.prev_sym; }
+        else {
+            const uint32_t e = lds_u32(K.t0 + ((bs.pre & K.m0) << 2));
+            bits_consume(bs, e, K.ring_base);
+            cur = e >> 8;
+            if (e & kL1Special) {
+                SlowSym r = huff_slow(bs, K.ring_base, e, P.flat[0], P.max_len[0]);
+                bs = r.bs; cur = r.sym;
+                if (cur == 0xFFFFFFFFu) terr = ETC1S_ERR_HUFFMAN | (PH_PRED_SYM << 4);
+                else if (cur == 256u) {                                           // mod.rs:268-275: run of the previous symbol
+                    r = vlc_decode(bs, K.ring_base, 4);
+                    bs = r.bs;
+                    if (r.sym == 0xFFFFFFFFu) terr = ETC1S_ERR_VLC | (PH_PRED_SYM << 4);
+                    st.pred_rep = r.sym + 3u - 1u;
+                    cur = st.prev_sym;
+                }
+            }
+            if (terr) tk[0] = make_uint2(kTokErr | ((terr & 15u) << 24) | ((terr >> 4) << 28), 0u);
+            cur &= 0xFFu;
+            st.prev_sym = cur;
+        }
     }
-    for (uint32_t i = lane; i < hist_size; i += 32) hist[i] = 0;                   // mod.rs:616-621
+    for (uint32_t j = 0; j < nblk && !terr; j++) {
+        const uint32_t pred = (cur >> (2u * j)) & 3u;
+        uint32_t d = 0u, tokA = pred << 16;
+        if (pred == 3u) {                                                         // mod.rs:340-353: DPCM delta symbol
+            const uint32_t e = lds_u32(K.t1 + ((bs.pre & K.m1) << 2));
+            bits_consume(bs, e, K.ring_base);
+            d = e >> 8;
+            if (e & kL1Special) {
+                const SlowSym r = huff_slow(bs, K.ring_base, e, P.flat[1], P.max_len[1]);
+                bs = r.bs; d = r.sym;
+                if (d == 0xFFFFFFFFu) terr = ETC1S_ERR_HUFFMAN | (PH_DELTA << 4);
+            }
+        }
+        if (K.is_video && pred == 2u) tokA |= kTokSkipSel;
+        else if (terr) { }
+        else if (st.sel_rle > 0u) { st.sel_rle--; tokA |= K.num_selectors; }      // mod.rs:370-372
+        else {
+            const uint32_t e = lds_u32(K.t2 + ((bs.pre & K.m2) << 2));
+            bits_consume(bs, e, K.ring_base);
+            uint32_t sym = e >> 8;
+            if (e & kL1Special) {
+                SlowSym r = huff_slow(bs, K.ring_base, e, P.flat[2], P.max_len[2]);
+                bs = r.bs; sym = r.sym;
+                if (sym == 0xFFFFFFFFu) terr = ETC1S_ERR_HUFFMAN | (PH_SELECTOR << 4);
+                else if (sym == K.rle_sym) {                                      // mod.rs:378-396
+                    const uint32_t e3 = lds_u32(K.t3 + ((bs.pre & K.m3) << 2));
+                    bits_consume(bs, e3, K.ring_base);
+                    uint32_t cnt = e3 >> 8;
+                    if (e3 & kL1Special) { r = huff_slow(bs, K.ring_base, e3, P.flat[3], P.max_len[3]); bs = r.bs; cnt = r.sym; }
+                    if (cnt == 0xFFFFFFFFu) terr = ETC1S_ERR_HUFFMAN | (PH_SELECTOR << 4);
+                    else {
+                        if (cnt == 63u) {
+                            r = vlc_decode(bs, K.ring_base, 7);
+                            bs = r.bs; cnt = r.sym;
+                            if (cnt == 0xFFFFFFFFu) terr = ETC1S_ERR_VLC | (PH_SELECTOR << 4);
+                        }
+                        st.sel_rle = 3u + cnt - 1u;
+                        sym = K.num_selectors;
+                    }
+                }
+            }
+            tokA |= sym & 0xFFFFu;
+        }
+        if (terr) tokA = (tokA & 0x30000u) | kTokErr | ((terr & 15u) << 24) | ((terr >> 4) << 28);
+        tk[j] = make_uint2(tokA, d);
+    }
+    st.bs = bs; st.cur = cur; st.terr = terr;
+    return st;
+}
+
+// Fast path for one pair of blocks of a non-video slice; returns false (state untouched) when the pair needs pair_slow.
+template <bool EVEN>
+__device__ __forceinline__ bool fast_pair(TokState& st, const TokConsts& K, uint2* tk)
+{
+    BitState bs = st.bs;
+    uint32_t spec = 0u, cur = st.cur, sel_rle = st.sel_rle, pred_rep = st.pred_rep, prev_sym = st.prev_sym;
+    if (EVEN) {
+        const uint32_t rep = pred_rep != 0u ? 1u : 0u;
+        const uint32_t e0 = lds_u32_if(K.t0 + ((bs.pre & K.m0) << 2), rep ^ 1u);
+        bits_consume(bs, e0, K.ring_base);
+        spec |= e0;
+        cur = rep ? prev_sym : ((e0 >> 8) & 0xFFu);
+        pred_rep -= rep;
+        prev_sym = cur;
+    }
+    uint2 t[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint32_t pred = (cur >> (2 * j)) & 3u;
+        const uint32_t e1 = lds_u32_if(K.t1 + ((bs.pre & K.m1) << 2), pred == 3u ? 1u : 0u);
+        bits_consume(bs, e1, K.ring_base);
+        const uint32_t run = sel_rle != 0u ? 1u : 0u;
+        const uint32_t e2 = lds_u32_if(K.t2 + ((bs.pre & K.m2) << 2), run ^ 1u);
+        bits_consume(bs, e2, K.ring_base);
+        spec |= e1 | e2;
+        sel_rle -= run;
+        t[j] = make_uint2((run ? K.num_selectors : (e2 >> 8)) | (pred << 16), e1 >> 8);
+    }
+    if (spec & kL1Special) return false;
+    tk[0] = t[0];
+    tk[1] = t[1];
+    st.bs = bs; st.cur = cur; st.sel_rle = sel_rle; st.pred_rep = pred_rep; st.prev_sym = prev_sym;
+    return true;
+}
+
+static __device__ void etc1s_tokenize(const Etc1sDecodeParams& P, const Etc1sSliceJob& job, PipeShared& W, const uint32_t* l1s,
+                                      unsigned long long* predrow, int lane, uint32_t trace_slice)
+{
+    const uint8_t* __restrict__ data = P.data + job.data_ofs;
+    const uint32_t nbx = job.nbx, nby = job.nby;
+    // (opaque(): the values are pinned in registers; left alone, ptxas re-derives them from the kernel parameters and the
+    // CTA's shared window -- S2UR / LDCU -- in front of every table read, which a lone warp pays in full)
+    auto opaque = [](uint32_t v) -> uint32_t { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; };
+    const uint32_t l1_base = smem_u32(l1s);
+    TokConsts K;
+    K.t0 = opaque(l1_base + 4u * P.l1_ofs[0]); K.t1 = opaque(l1_base + 4u * P.l1_ofs[1]);
+    K.t2 = opaque(l1_base + 4u * P.l1_ofs[2]); K.t3 = opaque(l1_base + 4u * P.l1_ofs[3]);
+    K.m0 = opaque((1u << P.l1_bits[0]) - 1u); K.m1 = opaque((1u << P.l1_bits[1]) - 1u);
+    K.m2 = opaque((1u << P.l1_bits[2]) - 1u); K.m3 = opaque((1u << P.l1_bits[3]) - 1u);
+    K.num_selectors = opaque(P.num_selectors & 0xFFFFu);
+    K.rle_sym = opaque((P.hist_size + K.num_selectors) & 0xFFFFu);                // mod.rs:220-222 (u16 arithmetic)
+    K.is_video = opaque(P.is_video);
+    uint32_t* ring = W.ring;
+    K.ring_base = opaque(smem_u32(ring));
+    const bool fast_ok = P.is_video == 0u;
+
     // prime the ring with the first three pieces
     uint32_t loaded = 0;                          // pieces [0, loaded) are (or were) in the ring
-    for (; loaded < 3; loaded++) { uint4 r[2]; piece_load(data, job.data_len, loaded, lane, r); piece_store(W.ring, loaded, lane, r); }
+    for (; loaded < 3; loaded++) { uint4 r[2]; piece_load(data, job.data_len, loaded, lane, r); piece_store(ring, loaded, lane, r); }
     __syncwarp();
 
-    BitState bs;
-    bs.buf = ((uint64_t)W.ring[1] << 32) | W.ring[0];
-    bs.avail = 64;
-    bs.nextw = 2;
-    uint32_t rover = hist_size / 2, sel_rle = 0, pred_rep = 0, prev_sym = 0, cur = 0, prev_ep = 0;
-    uint32_t err = 0, carry_up = 0;           // carry_up: previous row's endpoint index of block x0-1 (its slot is overwritten by then)
+    TokState st;
+    st.bs.lo = ring[0]; st.bs.hi = ring[1]; st.bs.pre = st.bs.lo; st.bs.avail = 64; st.bs.nw = ring[2]; st.bs.nextw = 3;
+    st.sel_rle = 0; st.pred_rep = 0; st.prev_sym = 0; st.cur = 0; st.terr = 0;
+    uint32_t round = 0;
+    K2T_DECL(const long long tt0 = clock64(); uint32_t n_slow = 0; uint32_t n_sym = 0; long long t_wait = 0;)
 
-    for (uint32_t y = 0; y < nby && !err; y++) {
-        for (uint32_t x0 = 0; x0 < nbx && !err; x0 += kRound) {
+    for (uint32_t y = 0; y < nby; y++) {
+        const bool even = (y & 1u) == 0u;
+        for (uint32_t x0 = 0; x0 < nbx; x0 += kRound, round++) {
             const uint32_t nb = nbx - x0 < (uint32_t)kRound ? nbx - x0 : (uint32_t)kRound;
-            // ---- cooperative: start fetching the next ring piece if the reader is about to need it ----
-            // reader position in pieces; pieces up to pos+2 must be resident before the next round starts
-            const uint32_t pos = (bs.nextw * 4u) / kHalfBytes;
+            const uint32_t slot = round % kTokRounds, use = round / kTokRounds;
+            if (round >= (uint32_t)kTokRounds) {                                  // the resolver must have read the slot's previous tokens
+                K2T_DECL(const long long w0 = clock64();)
+                while (!mbar_try_wait_once(&W.bar_empty[slot], (use - 1u) & 1u))
+                    if (ld_volatile_shared(&W.abort)) return;
+                K2T_DECL(t_wait += clock64() - w0;)
+            }
+            // start fetching the next ring piece if the reader is about to need it: pieces up to pos+2 must be resident
+            // before the next round starts
+            const uint32_t pos = (st.bs.nextw * 4u) / kHalfBytes;
             const bool fetch = loaded < pos + 3u;                                 // warp-uniform
             uint4 pre[2];
             if (fetch) piece_load(data, job.data_len, loaded, lane, pre);
-            // row above (x0-1 .. x0+31) into registers: lane l holds block x0 + l - 1, lane 0 of the next round's view via shfl
-            uint32_t up_mine = carry_up, up_last = 0;
-            if (y > 0) {
-                if (lane >= 1 && x0 + lane - 1 < nbx) up_mine = rowep[x0 + lane - 1];
-                if (x0 + 31 < nbx) up_last = rowep[x0 + 31];
+
+            uint2* tk = W.tok[slot];
+            unsigned long long nextp = 0ull;
+            unsigned long long curp = even ? 0ull : predrow[x0 >> 5];
+            const uint32_t npairs = (nb + 1u) >> 1;
+            if (even) {
+                for (uint32_t q = 0; q < npairs; q++) {
+                    const bool whole = 2u * q + 1u < nb;
+                    if (!(fast_ok && whole && fast_pair<true>(st, K, tk + 2u * q))) {
+                        K2T_DECL(n_slow++;)
+                        st = pair_slow(st, K, P, tk + 2u * q, whole ? 2u : 1u, 1u);
+                        if (st.terr) break;
+                    }
+                    nextp = (nextp >> 4) | ((unsigned long long)(st.cur >> 4) << 60);    // pair q ends up at bits 4q .. 4q+3
+                }
+                if (lane == 0) predrow[x0 >> 5] = nextp >> (4u * (16u - npairs));
+            } else {
+                for (uint32_t q = 0; q < npairs; q++) {
+                    const bool whole = 2u * q + 1u < nb;
+                    st.cur = (uint32_t)curp & 15u;
+                    curp >>= 4;
+                    if (!(fast_ok && whole && fast_pair<false>(st, K, tk + 2u * q))) {
+                        K2T_DECL(n_slow++;)
+                        st = pair_slow(st, K, P, tk + 2u * q, whole ? 2u : 1u, 0u);
+                        if (st.terr) break;
+                    }
+                }
+            }
+            K2T_DECL(n_sym += nb;)
+            if (fetch) { piece_store(ring, loaded, lane, pre); loaded++; }
+            __syncwarp();                                                         // tokens, ring piece and predictor row are visible to the warp
+            if (lane == 0) mbar_arrive(&W.bar_full[slot]);                        // release: the resolver's wait acquires
+            if (st.terr) return;
+        }
+    }
+    K2T(0, clock64() - tt0); K2T(1, t_wait); K2T(2, n_sym); K2T(3, n_slow);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stage 2: resolver warp.  rowep: endpoint index of every block of the previous row.
+// ---------------------------------------------------------------------------------------------------
+static __device__ void etc1s_resolve(const Etc1sDecodeParams& P, const Etc1sSliceJob& job, PipeShared& W, uint16_t* rowep, uint16_t* hist,
+                                     uint32_t* __restrict__ out, uint32_t* status, int lane, uint32_t trace_slice)
+{
+    const uint32_t nbx = job.nbx, nby = job.nby;
+    const uint32_t num_endpoints = P.num_endpoints, num_selectors = P.num_selectors, hist_size = P.hist_size;
+    const bool is_video = P.is_video != 0u;
+    // the scan needs (d + prev) mod n == the reference's 16-bit wrap-and-subtract: true when both terms are < n <= 32768
+    const bool scan_ok_n = num_endpoints <= 32768u;
+    for (uint32_t i = lane; i < hist_size; i += 32) hist[i] = 0;                   // mod.rs:616-621
+    __syncwarp();
+    uint32_t rover = hist_size / 2, prev_ep = 0, carry_up = 0, round = 0;
+    K2T_DECL(const long long tt0 = clock64(); long long t_wait = 0; uint32_t n_hit = 0; uint32_t n_serial = 0;)
+
+    for (uint32_t y = 0; y < nby; y++) {
+        for (uint32_t x0 = 0; x0 < nbx; x0 += kRound, round++) {
+            const uint32_t nb = nbx - x0 < (uint32_t)kRound ? nbx - x0 : (uint32_t)kRound;
+            const uint32_t slot = round % kTokRounds, use = round / kTokRounds;
+            const uint32_t x = x0 + lane;
+            // previous row (independent of the tokens: loaded while waiting)
+            uint32_t up = 0, upl = carry_up, up_last = 0;
+            if (y > 0u) {
+                if (x < nbx) up = rowep[x];
+                if (lane > 0 && x - 1u < nbx) upl = rowep[x - 1u];
+                if (x0 + 31u < nbx) up_last = rowep[x0 + 31u];
             }
             carry_up = up_last;
-            __syncwarp();                          // everyone has read the old row before it is overwritten below
-            uint32_t mine = 0;
-            // ---- serial chain, executed redundantly by every lane (mod.rs:245-455) ----
-            for (uint32_t b = 0; b < nb; b++) {
-                const uint32_t x = x0 + b;
-                if ((x & 1u) == 0u) {
-                    if ((y & 1u) == 0u) {
-                        if (pred_rep != 0u) { pred_rep--; cur = prev_sym; }
-                        else {
-                            const uint32_t s = huff_decode(bs, W.ring, hv[0], lane);
-                            if (s == 0xFFFFFFFFu) { err = ETC1S_ERR_HUFFMAN; break; }
-                            if (s == 256u) {
-                                uint32_t v;
-                                if (!vlc_decode(bs, W.ring, 4, v)) { err = ETC1S_ERR_VLC; break; }
-                                pred_rep = v + 3u - 1u;
-                                cur = prev_sym;
-                            } else { cur = s & 0xFFu; prev_sym = cur; }
-                        }
-                        if (lane == 0) predrow[x >> 1] = (uint8_t)(cur >> 4);
-                    } else cur = predrow[x >> 1];
+            K2T_DECL(const long long w0 = clock64();)
+            mbar_wait(&W.bar_full[slot], use & 1u);
+            K2T_DECL(t_wait += clock64() - w0;)
+            uint2 tok = make_uint2(0u, 0u);
+            if ((uint32_t)lane < nb) tok = W.tok[slot][lane];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&W.bar_empty[slot]);
+
+            const uint32_t errmask = __ballot_sync(0xFFFFFFFFu, (tok.x & kTokErr) != 0u);
+            const uint32_t nv = errmask ? (uint32_t)__ffs((int)errmask) - 1u : nb;  // lanes < nv hold complete tokens
+            const uint32_t pred = (tok.x >> 16) & 3u, d = tok.y;
+            uint32_t key = 0xFFFFFFFFu;                                              // (block << 3 | phase) << 8 | code of this lane's first error
+            if (errmask && (uint32_t)lane == nv) key = (((uint32_t)lane << 3 | ((tok.x >> 28) & 7u)) << 8) | ((tok.x >> 24) & 15u);
+            const bool has_pred = (uint32_t)lane < nv || (errmask && (uint32_t)lane == nv && ((tok.x >> 28) & 7u) > (uint32_t)PH_PRED_CHECK);
+            if (has_pred) {                                                          // asserts mod.rs:304-339
+                const bool bad = (pred == 0u && x == 0u) || (pred == 1u && y == 0u) || (pred == 2u && !is_video && (x == 0u || y == 0u));
+                if (bad) { const uint32_t k2 = (((uint32_t)lane << 3 | PH_PRED_CHECK) << 8) | ETC1S_ERR_PREDICTION; key = k2 < key ? k2 : key; }
+            }
+
+            // ---- endpoints: f_b(prev) = const c (up / up-left / video 0), prev (left) or (prev + d) mod n ----
+            uint32_t ep;
+            const bool live = (uint32_t)lane < nv;
+            const bool scan_ok = scan_ok_n && !__any_sync(0xFFFFFFFFu, live && pred == 3u && d >= num_endpoints);
+            if (scan_ok) {
+                uint32_t f = 0u;                                                     // bit 31: constant; low bits: value
+                if (live) f = pred == 1u ? (0x80000000u | up) : pred == 2u ? (0x80000000u | (is_video ? 0u : upl)) : pred == 3u ? d : 0u;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t g = __shfl_up_sync(0xFFFFFFFFu, f, o);
+                    if (lane >= o && !(f >> 31)) {
+                        uint32_t v = (g & 0x7FFFFFFFu) + f;
+                        if (v >= num_endpoints) v -= num_endpoints;
+                        f = (g & 0x80000000u) | v;
+                    }
                 }
-                const uint32_t pred = cur & 3u;
-                cur >>= 2;
-                uint32_t ep;
-                if (pred == 0u) { if (x == 0u) { err = ETC1S_ERR_PREDICTION; break; } ep = prev_ep; }
-                else if (pred == 1u) {
-                    if (y == 0u) { err = ETC1S_ERR_PREDICTION; break; }
-                    ep = b == 31u ? up_last : __shfl_sync(0xFFFFFFFFu, up_mine, b + 1);
+                ep = f & 0x7FFFFFFFu;
+                if (!(f >> 31)) { ep += prev_ep; if (ep >= num_endpoints) ep -= num_endpoints; }
+            } else {
+                ep = 0;
+                K2T_DECL(n_serial++;)
+                uint32_t pe = prev_ep;
+                for (uint32_t b = 0; b < nv; b++) {                                  // the reference's own arithmetic, block by block
+                    const uint32_t pb = __shfl_sync(0xFFFFFFFFu, pred, b), db = __shfl_sync(0xFFFFFFFFu, d, b);
+                    const uint32_t ub = __shfl_sync(0xFFFFFFFFu, up, b), ulb = __shfl_sync(0xFFFFFFFFu, upl, b);
+                    uint32_t e;
+                    if (pb == 0u) e = pe;
+                    else if (pb == 1u) e = ub;
+                    else if (pb == 2u) e = is_video ? 0u : ulb;
+                    else { e = (db + pe) & 0xFFFFu; if (e >= num_endpoints) e = (e - num_endpoints) & 0xFFFFu; }
+                    pe = e;
+                    if ((uint32_t)lane == b) ep = e;
                 }
-                else if (pred == 2u) {
-                    if (P.is_video) ep = 0u;                                      // quirk C-5: previous-frame state is always zero
-                    else { if (x == 0u || y == 0u) { err = ETC1S_ERR_PREDICTION; break; } ep = __shfl_sync(0xFFFFFFFFu, up_mine, b); }
+            }
+            if (nv > 0u) prev_ep = __shfl_sync(0xFFFFFFFFu, ep, nv - 1u);
+
+            // ---- selectors: the history buffer is the serial part (mod.rs:399-426, :610-640) ----
+            uint32_t sel = 0u;
+            if (!is_video && hist_size > 0u && hist_size <= 64u && nv == (uint32_t)kRound) {
+                uint16_t* hs = W.hist;                                               // (named so that the accesses compile to LDS / STS)
+                // straight-line form for full rounds: a codebook index is "store sym at the rover", a history reference is
+                // "swap entries k and k/2" (k = 0 swaps with itself); both are two loads and two stores at selected addresses
+                uint32_t herr = 32u;
+#pragma unroll 8
+                for (uint32_t b = 0; b < (uint32_t)kRound; b++) {
+                    const uint32_t sym = __shfl_sync(0xFFFFFFFFu, tok.x, b) & 0xFFFFu;
+                    const bool hit = sym >= num_selectors;
+                    uint32_t k = sym - num_selectors;
+                    const bool bad = hit && k >= hist_size;                          // assert mod.rs:409
+                    herr = bad && b < herr ? b : herr;
+                    k = hit && !bad ? k : rover;
+                    const uint32_t kh = hit ? k >> 1 : rover;
+                    const uint32_t v = hs[k], t = hs[kh];
+                    hs[k] = (uint16_t)(hit ? t : sym);                               // every lane stores the same values
+                    hs[kh] = (uint16_t)(hit ? v : sym);
+                    const uint32_t s = hit ? v : sym;
+                    const uint32_t r1 = rover + 1u == hist_size ? hist_size / 2 : rover + 1u;
+                    rover = hit ? rover : r1;
+                    if ((uint32_t)lane == b) sel = s;
+                }
+                if (herr < 32u && (uint32_t)lane == herr) { const uint32_t k5 = ((herr << 3 | PH_HISTORY) << 8) | ETC1S_ERR_PREDICTION; key = k5 < key ? k5 : key; }
+            } else
+            for (uint32_t b = 0; b < nv; b++) {
+                const uint32_t a = __shfl_sync(0xFFFFFFFFu, tok.x, b);
+                const uint32_t sym = a & 0xFFFFu;
+                uint32_t s = 0u;
+                if (a & kTokSkipSel) s = 0u;                                         // quirk C-5: previous-frame state is always zero
+                else if (sym >= num_selectors) {
+                    const uint32_t k = sym - num_selectors;
+                    if (hist_size == 0u || k >= hist_size) {                         // asserts mod.rs:404,409
+                        if ((uint32_t)lane == b) { const uint32_t k5 = ((b << 3 | PH_HISTORY) << 8) | ETC1S_ERR_PREDICTION; key = k5 < key ? k5 : key; }
+                        break;
+                    }
+                    s = hist[k];
+                    K2T_DECL(n_hit++;)
+                    if (k != 0u) { const uint16_t t = hist[k >> 1]; hist[k >> 1] = (uint16_t)s; hist[k] = t; }     // every lane stores the same values
                 } else {
-                    const uint32_t d = huff_decode(bs, W.ring, hv[1], lane);
-                    if (d == 0xFFFFFFFFu) { err = ETC1S_ERR_HUFFMAN; break; }
-                    ep = (d + prev_ep) & 0xFFFFu;
-                    if (ep >= num_endpoints) ep = (ep - num_endpoints) & 0xFFFFu;
+                    s = sym;
+                    if (hist_size > 0u) { hist[rover] = (uint16_t)sym; rover++; if (rover == hist_size) rover = hist_size / 2; }
                 }
-                prev_ep = ep;
-                uint32_t sel;
-                if (!P.is_video || pred != 2u) {
-                    uint32_t sym;
-                    if (sel_rle > 0u) { sel_rle--; sym = num_selectors; }
-                    else {
-                        sym = huff_decode(bs, W.ring, hv[2], lane);
-                        if (sym == 0xFFFFFFFFu) { err = ETC1S_ERR_HUFFMAN; break; }
-                        if (sym == rle_sym) {
-                            const uint32_t r = huff_decode(bs, W.ring, hv[3], lane);
-                            if (r == 0xFFFFFFFFu) { err = ETC1S_ERR_HUFFMAN; break; }
-                            uint32_t cnt = 3u + r;
-                            if (r == 63u) {
-                                uint32_t v;
-                                if (!vlc_decode(bs, W.ring, 7, v)) { err = ETC1S_ERR_VLC; break; }
-                                cnt = 3u + v;
-                            }
-                            sel_rle = cnt - 1u;
-                            sym = num_selectors;
-                        }
-                    }
-                    if (sym >= num_selectors) {
-                        const uint32_t k = sym - num_selectors;
-                        if (hist_size == 0u || k >= hist_size) { err = ETC1S_ERR_PREDICTION; break; }     // asserts mod.rs:404,409
-                        sel = hist[k];
-                        if (k != 0u) { const uint16_t a = hist[k >> 1]; __syncwarp(); if (lane == 0) { hist[k >> 1] = (uint16_t)sel; hist[k] = a; } __syncwarp(); }
-                    } else {
-                        sel = sym;
-                        if (hist_size > 0u) { if (lane == 0) hist[rover] = (uint16_t)sym; rover++; if (rover == hist_size) rover = hist_size / 2; __syncwarp(); }
-                    }
-                } else sel = 0u;
-                if (ep >= num_endpoints || sel >= num_selectors) { err = ETC1S_ERR_RANGE; break; }        // asserts mod.rs:443-444
-                if ((uint32_t)lane == b) mine = ep | (sel << 16);
+                if ((uint32_t)lane == b) sel = s;
             }
-            // ---- cooperative: flush the decoded pairs, update the row state, land the prefetched ring piece ----
-            if (!err && (uint32_t)lane < nb) {
-                out[(uint64_t)y * nbx + x0 + lane] = mine;
-                rowep[x0 + lane] = (uint16_t)mine;
+            if (live && (ep >= num_endpoints || sel >= num_selectors)) {             // asserts mod.rs:443-444
+                const uint32_t k6 = (((uint32_t)lane << 3 | PH_RANGE) << 8) | ETC1S_ERR_RANGE;
+                key = k6 < key ? k6 : key;
             }
-            if (fetch) { piece_store(W.ring, loaded, lane, pre); loaded++; }
+            if (__any_sync(0xFFFFFFFFu, key != 0xFFFFFFFFu)) {
+                const uint32_t first = __reduce_min_sync(0xFFFFFFFFu, key);
+                if (lane == 0) { *status = first & 0xFFu; *reinterpret_cast<volatile uint32_t*>(&W.abort) = 1u; }
+                return;
+            }
+            __syncwarp();                                                            // everyone has read the old row before it is overwritten
+            if ((uint32_t)lane < nb) {
+                out[(uint64_t)y * nbx + x] = ep | (sel << 16);
+                rowep[x] = (uint16_t)ep;
+            }
             __syncwarp();
         }
     }
-    if (lane == 0) P.status[slice] = err;
+    if (lane == 0) *status = 0u;
+    K2T(4, clock64() - tt0); K2T(5, t_wait); K2T(6, n_hit); K2T(7, n_serial);
+}
+
+// `pipes` slice pipelines per CTA: warps [0, pipes) tokenize, warps [pipes, 2 pipes) resolve.  The per-slice row state
+// lives in shared memory when the slice is at most `row_cap` blocks wide, else in the global scratch area.
+__global__ void __launch_bounds__(512) etc1s_entropy_decode_kernel(const __grid_constant__ Etc1sDecodeParams P, uint32_t pipes, uint32_t row_cap)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* l1s = reinterpret_cast<uint32_t*>(smem_raw);
+    const uint32_t l1_words = P.l1_ofs[4];
+    PipeShared* pipe_all = reinterpret_cast<PipeShared*>(smem_raw + (((size_t)l1_words * 4 + 15) & ~(size_t)15));
+    unsigned char* rows_all = reinterpret_cast<unsigned char*>(pipe_all + pipes);
+    for (uint32_t i = threadIdx.x; i < l1_words; i += blockDim.x) l1s[i] = P.l1[i];
+    if (threadIdx.x < pipes) {
+        PipeShared& W = pipe_all[threadIdx.x];
+        for (int r = 0; r < kTokRounds; r++) { mbar_init(&W.bar_full[r], 1); mbar_init(&W.bar_empty[r], 1); }
+        W.abort = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t pipe = warp % pipes, role = warp / pipes;
+    const uint32_t slice = blockIdx.x * pipes + pipe;
+    if (slice >= P.num_slices) return;
+    PipeShared& W = pipe_all[pipe];
+    const Etc1sSliceJob job = P.jobs[slice];
+    const size_t row_bytes = etc1s_row_state_bytes(row_cap);
+    unsigned char* rows = job.nbx <= row_cap ? rows_all + (size_t)pipe * row_bytes : P.scratch + job.scratch_ofs;
+    uint16_t* rowep = reinterpret_cast<uint16_t*>(rows);
+    unsigned long long* predrow = reinterpret_cast<unsigned long long*>(rows + ((((size_t)job.nbx + 7u) & ~(size_t)7u) * 2u));
+    if (job.nbx <= row_cap) predrow = reinterpret_cast<unsigned long long*>(rows + ((((size_t)row_cap + 7u) & ~(size_t)7u) * 2u));
+    uint16_t* hist = P.hist_size <= 64u ? W.hist : reinterpret_cast<uint16_t*>(P.scratch + job.scratch_ofs + etc1s_row_state_bytes(job.nbx));
+    if (role == 0u) etc1s_tokenize(P, job, W, l1s, predrow, lane, slice);
+    else etc1s_resolve(P, job, W, rowep, hist, P.out_idx + job.out_ofs, P.status + slice, lane, slice);
 }
 
 // K3a: mod.rs:163-181 -- ETC1S block = [R5<<3, G5<<3, B5<<3, inten<<5 | inten<<2 | 3, selector etc1 bytes]
@@ -349,23 +645,25 @@ __global__ void __launch_bounds__(256) etc1s_gather_rgba_kernel(const uint32_t* 
     }
 }
 
-// shared memory of K2: 4 first-level tables + sorted symbols + per warp {ring, history, previous-row state for row_cap blocks}
-static size_t etc1s_decode_smem_bytes(int warps, uint32_t row_cap, uint32_t sym_bytes)
+// shared memory of K2: first-level tables + per pipeline {PipeShared, previous-row state for row_cap blocks}
+static size_t etc1s_decode_smem_bytes(uint32_t l1_words, int pipes, uint32_t row_cap)
 {
-    return 4 * kL1Size * sizeof(uint32_t) + sym_bytes + (size_t)warps * (sizeof(WarpShared) + ((size_t)row_cap + row_cap / 2 + 8) * 2);
+    return (((size_t)l1_words * 4 + 15) & ~(size_t)15) + (size_t)pipes * (sizeof(PipeShared) + etc1s_row_state_bytes(row_cap));
 }
 
-cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, int warps_per_cta, uint32_t max_nbx, cudaStream_t stream)
+cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, int slices_per_cta, uint32_t max_nbx, int sm_count, cudaStream_t stream)
 {
     if (P.num_slices == 0) return cudaSuccess;
-    const size_t limit = 220 * 1024;
-    // sorted symbols in shared memory when they fit in 96 KiB (codebooks up to ~24k entries each), else read from global
-    uint32_t sym_bytes = ((P.sym_ofs[4] * 2u) + 15u) & ~15u;
-    if (sym_bytes > 96 * 1024) sym_bytes = 0;
+    const size_t limit = 224 * 1024;
+    const uint32_t l1_words = P.l1_ofs[4];
     // previous-row state in shared memory when it fits, else in the scratch area
-    uint32_t row_cap = (max_nbx + 7u) & ~7u;
-    if (etc1s_decode_smem_bytes(1, row_cap, sym_bytes) > limit) row_cap = 0;
-    while (warps_per_cta > 1 && etc1s_decode_smem_bytes(warps_per_cta, row_cap, sym_bytes) > limit) warps_per_cta >>= 1;
+    uint32_t row_cap = (max_nbx + 31u) & ~31u;
+    if (etc1s_decode_smem_bytes(l1_words, 1, row_cap) > limit) row_cap = 0;
+    // spread the slices over the SMs first; pack pipelines (which share the tables) only when there are more slices than SMs
+    int pipes = slices_per_cta > 0 ? slices_per_cta : (int)((P.num_slices + (uint32_t)sm_count - 1u) / (uint32_t)sm_count);
+    if (pipes > 8) pipes = 8;                                 // 512 threads: the tokenizer wants more than 64 registers
+    while (pipes > 1 && etc1s_decode_smem_bytes(l1_words, pipes, row_cap) > limit) pipes--;
+    if (etc1s_decode_smem_bytes(l1_words, pipes, row_cap) > limit) return cudaErrorInvalidValue;     // the host sizes the tables to fit
     static bool configured[16] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -374,10 +672,18 @@ cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, int warps_per_cta, u
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    const unsigned grid = (P.num_slices + warps_per_cta - 1) / warps_per_cta;
-    etc1s_entropy_decode_kernel<<<grid, 32 * warps_per_cta, etc1s_decode_smem_bytes(warps_per_cta, row_cap, sym_bytes), stream>>>(P, row_cap, sym_bytes);
+    const unsigned grid = (P.num_slices + pipes - 1) / pipes;
+    etc1s_entropy_decode_kernel<<<grid, 64 * pipes, etc1s_decode_smem_bytes(l1_words, pipes, row_cap), stream>>>(P, (uint32_t)pipes, row_cap);
     return cudaGetLastError();
 }
+
+#ifdef B2BU_K2_TRACE
+extern "C" __attribute__((visibility("default"))) int b2bu_debug_k2_trace(unsigned long long* dst, int reset)
+{
+    if (reset) { static unsigned long long z[64][8]; return (int)cudaMemcpyToSymbol(g_k2trace, z, sizeof z); }
+    return (int)cudaMemcpyFromSymbol(dst, g_k2trace, sizeof(unsigned long long) * 64 * 8);
+}
+#endif
 
 cudaError_t launch_etc1s_gather_etc1(const uint32_t* idx, uint64_t nblocks, const uint32_t* endpoints, const uint32_t* sel_etc1, void* out,
                                      int sm_count, cudaStream_t stream)

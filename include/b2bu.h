@@ -136,6 +136,11 @@ int b2bu_etc1s_transcode_slices(b2bu_etc1s* h, int target, uint32_t nbx, uint32_
  * reported separately because K2 is a latency-bound serial chain per slice while K3 is HBM-bound. */
 int b2bu_etc1s_last_timing(b2bu_etc1s* h, float* entropy_ms, float* gather_ms, float* d2h_ms, uint64_t* blocks);
 
+/* How the four slice Huffman models (huffman.rs:133-184; endpoint predictor, delta endpoint, selector, selector
+ * run length) sit in K2's shared memory: width in bits of each first-level table and each model's longest code
+ * (codes longer than the first-level width are looked up in the flat table in global memory). */
+int b2bu_etc1s_table_info(b2bu_etc1s* h, uint32_t l1_bits[4], uint32_t max_code_len[4]);
+
 /* ---- file level: src/basis.rs:8-260, src/lib.rs:63-79 ---------------------------------------- */
 typedef struct b2bu_header {       /* basis.rs:419-454 (all 26 fields, widened to u32) */
     uint32_t sig, ver, header_size, header_crc16, data_size, data_crc16, total_slices, total_images, tex_format,
