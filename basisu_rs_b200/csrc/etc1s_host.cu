@@ -19,8 +19,10 @@ namespace b2bu {
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
 
-// shared memory given to the four first-level Huffman tables of K2 (the rest holds the per-slice pipelines)
-constexpr size_t kL1BudgetBytes = 128 * 1024;
+// Shared memory given to the four first-level Huffman tables of K2 (the rest holds the per-slice pipelines).  Two sets are
+// kept per file: a wide one for launches with one slice per SM (a lone pipeline leaves ~210 KB free) and a narrow one for
+// batches that pack several slice pipelines into a CTA.
+constexpr size_t kL1BudgetBytes[2] = {96 * 1024, 208 * 1024};
 
 // ---- bit cursor: LSB first, bytes past the end read as zero (src/bitreader.rs:27-60) ----------
 struct BitCursor {
@@ -182,8 +184,10 @@ struct b2bu_etc1s {
     uint32_t* d_endpoints = nullptr;     // inten | r5 << 8 | g5 << 16 | b5 << 24
     uint32_t* d_sel_plain = nullptr;     // 4 rows, 2 bits per x          (etc.rs:343-361)
     uint32_t* d_sel_etc1 = nullptr;      // ETC1 bit planes               (etc.rs:363-393)
-    uint32_t* d_l1 = nullptr;            // the four first-level tables back to back
-    uint32_t l1_bits[4] = {0, 0, 0, 0}, l1_ofs[5] = {0, 0, 0, 0, 0};
+    // [0] narrow / [1] wide set of the four first-level tables, back to back
+    uint32_t* d_l1[2] = {nullptr, nullptr};
+    uint32_t l1_bits[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, l1_ofs[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    int last_set = 0;                    // table set used by the last call
     uint32_t* d_flat[4] = {nullptr, nullptr, nullptr, nullptr};
     // per-call scratch (grow only)
     void* d_data = nullptr; size_t data_cap = 0;
@@ -268,12 +272,15 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
     P.num_slices = (uint32_t)ns;
     P.out_idx = static_cast<uint32_t*>(h->d_idx);
     P.scratch = static_cast<uint8_t*>(h->d_scratch);
-    P.l1 = h->d_l1;
-    for (int t = 0; t < 4; t++) { P.flat[t] = h->d_flat[t]; P.max_len[t] = h->max_len[t]; P.l1_bits[t] = h->l1_bits[t]; P.l1_ofs[t] = h->l1_ofs[t]; }
-    P.l1_ofs[4] = h->l1_ofs[4];
+    const Etc1sDecodePlan dplan = plan_etc1s_decode((uint32_t)ns, max_nbx, c->sm_count, h->l1_ofs[0][4], h->l1_ofs[1][4]);
+    const int set = dplan.big_tables ? 1 : 0;
+    h->last_set = set;
+    P.l1 = h->d_l1[set];
+    for (int t = 0; t < 4; t++) { P.flat[t] = h->d_flat[t]; P.max_len[t] = h->max_len[t]; P.l1_bits[t] = h->l1_bits[set][t]; P.l1_ofs[t] = h->l1_ofs[set][t]; }
+    P.l1_ofs[4] = h->l1_ofs[set][4];
     P.num_endpoints = h->num_endpoints; P.num_selectors = h->num_selectors; P.hist_size = h->hist_size; P.is_video = h->is_video ? 1u : 0u;
     P.status = static_cast<uint32_t*>(h->d_status);
-    CK(launch_etc1s_decode(P, 0, max_nbx, c->sm_count, s));
+    CK(launch_etc1s_decode(P, dplan, s));
     count_launch(1);
     CK(cudaEventRecord(h->ev[1], s));
 
@@ -369,20 +376,22 @@ static int etc1s_open_impl(uint32_t endpoint_count, uint32_t selector_count, con
         for (int t = 0; t < 4; t++) if ((st = read_huffman_table(bc, models[t]))) return st;
         h->hist_size = bc.read(13);
     }
-    unsigned bits[4];
-    choose_l1_bits(models, kL1BudgetBytes, bits);
-    std::vector<uint32_t> l1;
+    std::vector<uint32_t> l1[2];
     const uint32_t run_sym[4] = {256u, 0xFFFFFFFFu, (h->hist_size + selector_count) & 0xFFFFu, 0xFFFFFFFFu};   // mod.rs:220-222
-    for (int t = 0; t < 4; t++) {
-        h->l1_bits[t] = bits[t]; h->l1_ofs[t] = (uint32_t)l1.size(); h->max_len[t] = models[t].max_len;
-        l1.resize(l1.size() + ((size_t)1 << bits[t]));
-        build_l1(models[t], bits[t], run_sym[t], l1.data() + h->l1_ofs[t]);
+    for (int set = 0; set < 2; set++) {
+        unsigned bits[4];
+        choose_l1_bits(models, kL1BudgetBytes[set], bits);
+        for (int t = 0; t < 4; t++) {
+            h->l1_bits[set][t] = bits[t]; h->l1_ofs[set][t] = (uint32_t)l1[set].size(); h->max_len[t] = models[t].max_len;
+            l1[set].resize(l1[set].size() + ((size_t)1 << bits[t]));
+            build_l1(models[t], bits[t], run_sym[t], l1[set].data() + h->l1_ofs[set][t]);
+        }
+        h->l1_ofs[set][4] = (uint32_t)l1[set].size();
     }
-    h->l1_ofs[4] = (uint32_t)l1.size();
 
     CK(cudaSetDevice(h->device));
     if ((st = upload(&h->d_endpoints, endpoints)) || (st = upload(&h->d_sel_plain, sel_plain)) || (st = upload(&h->d_sel_etc1, sel_etc1)) ||
-        (st = upload(&h->d_l1, l1))) return st;
+        (st = upload(&h->d_l1[0], l1[0])) || (st = upload(&h->d_l1[1], l1[1]))) return st;
     for (int t = 0; t < 4; t++) if ((st = upload(&h->d_flat[t], models[t].flat))) return st;
     *out = h.release();
     return B2BU_OK;
@@ -442,7 +451,7 @@ void b2bu_etc1s_close(b2bu_etc1s* h)
     if (!h) return;
     cudaSetDevice(h->device);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    cudaFree(h->d_endpoints); cudaFree(h->d_sel_plain); cudaFree(h->d_sel_etc1); cudaFree(h->d_l1);
+    cudaFree(h->d_endpoints); cudaFree(h->d_sel_plain); cudaFree(h->d_sel_etc1); cudaFree(h->d_l1[0]); cudaFree(h->d_l1[1]);
     for (int t = 0; t < 4; t++) cudaFree(h->d_flat[t]);
     cudaFree(h->d_data); cudaFree(h->d_idx); cudaFree(h->d_out); cudaFree(h->d_scratch); cudaFree(h->d_jobs); cudaFree(h->d_status);
     delete h;
@@ -462,7 +471,7 @@ int b2bu_etc1s_last_timing(b2bu_etc1s* h, float* entropy_ms, float* gather_ms, f
 int b2bu_etc1s_table_info(b2bu_etc1s* h, uint32_t l1_bits[4], uint32_t max_code_len[4])
 {
     if (!h) return B2BU_ERR_ARGUMENT;
-    for (int t = 0; t < 4; t++) { if (l1_bits) l1_bits[t] = h->l1_bits[t]; if (max_code_len) max_code_len[t] = h->max_len[t]; }
+    for (int t = 0; t < 4; t++) { if (l1_bits) l1_bits[t] = h->l1_bits[h->last_set][t]; if (max_code_len) max_code_len[t] = h->max_len[t]; }
     return B2BU_OK;
 }
 

@@ -47,7 +47,7 @@ constexpr uint32_t kTokErr = 1u << 31;            // tokenizer stopped here: cod
 // selector symbols (4), history asserts (5), final range asserts (6)
 enum { PH_PRED_SYM = 1, PH_PRED_CHECK = 2, PH_DELTA = 3, PH_SELECTOR = 4, PH_HISTORY = 5, PH_RANGE = 6 };
 
-struct PipeShared {
+struct alignas(16) PipeShared {
     uint32_t ring[kRingWords];                    // compressed bytes of the slice (tokenizer)
     uint2 tok[kTokRounds][kRound];                // tokenizer -> resolver
     uint16_t hist[64];                            // selector history when it fits (it always does for real files)
@@ -268,38 +268,46 @@ __device__ __noinline__ TokState pair_slow(TokState st, const TokConsts K, const
     return st;
 }
 
-// Fast path for one pair of blocks of a non-video slice; returns false (state untouched) when the pair needs pair_slow.
-template <bool EVEN>
-__device__ __forceinline__ bool fast_pair(TokState& st, const TokConsts& K, uint2* tk)
+// Fast path for NP consecutive pairs of blocks of a non-video slice; returns false (state untouched, no tokens written)
+// when one of them needs pair_slow.  EVEN: the pairs start with their 2x2 group's predictor symbol and `grp` receives
+// the NP symbols (8 bits each, first pair lowest); else `grp` supplies 4 predictor bits per pair.
+template <bool EVEN, int NP>
+__device__ __forceinline__ bool fast_pairs(TokState& st, const TokConsts& K, uint2* tk, uint32_t& grp)
 {
     BitState bs = st.bs;
-    uint32_t spec = 0u, cur = st.cur, sel_rle = st.sel_rle, pred_rep = st.pred_rep, prev_sym = st.prev_sym;
-    if (EVEN) {
-        const uint32_t rep = pred_rep != 0u ? 1u : 0u;
-        const uint32_t e0 = lds_u32_if(K.t0 + ((bs.pre & K.m0) << 2), rep ^ 1u);
-        bits_consume(bs, e0, K.ring_base);
-        spec |= e0;
-        cur = rep ? prev_sym : ((e0 >> 8) & 0xFFu);
-        pred_rep -= rep;
-        prev_sym = cur;
-    }
-    uint2 t[2];
+    uint32_t spec = 0u, sel_rle = st.sel_rle, pred_rep = st.pred_rep, prev_sym = st.prev_sym, syms = 0u;
+    uint2 t[2 * NP];
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-        const uint32_t pred = (cur >> (2 * j)) & 3u;
-        const uint32_t e1 = lds_u32_if(K.t1 + ((bs.pre & K.m1) << 2), pred == 3u ? 1u : 0u);
-        bits_consume(bs, e1, K.ring_base);
-        const uint32_t run = sel_rle != 0u ? 1u : 0u;
-        const uint32_t e2 = lds_u32_if(K.t2 + ((bs.pre & K.m2) << 2), run ^ 1u);
-        bits_consume(bs, e2, K.ring_base);
-        spec |= e1 | e2;
-        sel_rle -= run;
-        t[j] = make_uint2((run ? K.num_selectors : (e2 >> 8)) | (pred << 16), e1 >> 8);
+    for (int q = 0; q < NP; q++) {
+        uint32_t cur;
+        if (EVEN) {
+            const uint32_t rep = pred_rep != 0u ? 1u : 0u;
+            const uint32_t e0 = lds_u32_if(K.t0 + ((bs.pre & K.m0) << 2), rep ^ 1u);
+            bits_consume(bs, e0, K.ring_base);
+            spec |= e0;
+            cur = rep ? prev_sym : ((e0 >> 8) & 0xFFu);
+            pred_rep -= rep;
+            prev_sym = cur;
+            syms |= cur << (8 * q);
+        } else cur = (grp >> (4 * q)) & 15u;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const uint32_t pred = (cur >> (2 * j)) & 3u;
+            const uint32_t e1 = lds_u32_if(K.t1 + ((bs.pre & K.m1) << 2), pred == 3u ? 1u : 0u);
+            bits_consume(bs, e1, K.ring_base);
+            const uint32_t run = sel_rle != 0u ? 1u : 0u;
+            const uint32_t e2 = lds_u32_if(K.t2 + ((bs.pre & K.m2) << 2), run ^ 1u);
+            bits_consume(bs, e2, K.ring_base);
+            spec |= e1 | e2;
+            sel_rle -= run;
+            t[2 * q + j] = make_uint2((run ? K.num_selectors : (e2 >> 8)) | (pred << 16), e1 >> 8);
+        }
     }
     if (spec & kL1Special) return false;
-    tk[0] = t[0];
-    tk[1] = t[1];
-    st.bs = bs; st.cur = cur; st.sel_rle = sel_rle; st.pred_rep = pred_rep; st.prev_sym = prev_sym;
+#pragma unroll
+    for (int i = 0; i < 2 * NP; i += 2) *reinterpret_cast<uint4*>(tk + i) = make_uint4(t[i].x, t[i].y, t[i + 1].x, t[i + 1].y);
+    st.bs = bs; st.sel_rle = sel_rle; st.pred_rep = pred_rep; st.prev_sym = prev_sym;
+    if (EVEN) grp = syms;
     return true;
 }
 
@@ -357,27 +365,45 @@ static __device__ void etc1s_tokenize(const Etc1sDecodeParams& P, const Etc1sSli
             unsigned long long nextp = 0ull;
             unsigned long long curp = even ? 0ull : predrow[x0 >> 5];
             const uint32_t npairs = (nb + 1u) >> 1;
-            if (even) {
-                for (uint32_t q = 0; q < npairs; q++) {
-                    const bool whole = 2u * q + 1u < nb;
-                    if (!(fast_ok && whole && fast_pair<true>(st, K, tk + 2u * q))) {
-                        K2T_DECL(n_slow++;)
-                        st = pair_slow(st, K, P, tk + 2u * q, whole ? 2u : 1u, 1u);
-                        if (st.terr) break;
+            constexpr int NP = 2;                                                 // pairs per fast-path step
+            if (fast_ok && nb == (uint32_t)kRound) {
+                // full round: 8 straight-line steps of 4 blocks; a step that meets anything unusual is redone pair by pair
+                if (even) {
+                    for (uint32_t q = 0; q < (uint32_t)kRound / 2; q += NP) {
+                        uint32_t grp = 0u;
+                        if (!fast_pairs<true, NP>(st, K, tk + 2u * q, grp)) {
+                            K2T_DECL(n_slow++;)
+                            for (int i = 0; i < NP && !st.terr; i++) { st = pair_slow(st, K, P, tk + 2u * (q + i), 2u, 1u); grp |= st.cur << (8 * i); }
+                            if (st.terr) break;
+                        }
+#pragma unroll
+                        for (int i = 0; i < NP; i++) nextp = (nextp >> 4) | ((unsigned long long)((grp >> (8 * i + 4)) & 15u) << 60);
                     }
+                    if (lane == 0) predrow[x0 >> 5] = nextp;
+                } else {
+                    for (uint32_t q = 0; q < (uint32_t)kRound / 2; q += NP) {
+                        uint32_t grp = (uint32_t)curp & ((1u << (4 * NP)) - 1u);
+                        curp >>= 4 * NP;
+                        if (!fast_pairs<false, NP>(st, K, tk + 2u * q, grp)) {
+                            K2T_DECL(n_slow++;)
+                            for (int i = 0; i < NP && !st.terr; i++) { st.cur = (grp >> (4 * i)) & 15u; st = pair_slow(st, K, P, tk + 2u * (q + i), 2u, 0u); }
+                            if (st.terr) break;
+                        }
+                    }
+                }
+            } else if (even) {
+                for (uint32_t q = 0; q < npairs; q++) {
+                    st = pair_slow(st, K, P, tk + 2u * q, 2u * q + 1u < nb ? 2u : 1u, 1u);
+                    if (st.terr) break;
                     nextp = (nextp >> 4) | ((unsigned long long)(st.cur >> 4) << 60);    // pair q ends up at bits 4q .. 4q+3
                 }
                 if (lane == 0) predrow[x0 >> 5] = nextp >> (4u * (16u - npairs));
             } else {
                 for (uint32_t q = 0; q < npairs; q++) {
-                    const bool whole = 2u * q + 1u < nb;
                     st.cur = (uint32_t)curp & 15u;
                     curp >>= 4;
-                    if (!(fast_ok && whole && fast_pair<false>(st, K, tk + 2u * q))) {
-                        K2T_DECL(n_slow++;)
-                        st = pair_slow(st, K, P, tk + 2u * q, whole ? 2u : 1u, 0u);
-                        if (st.terr) break;
-                    }
+                    st = pair_slow(st, K, P, tk + 2u * q, 2u * q + 1u < nb ? 2u : 1u, 0u);
+                    if (st.terr) break;
                 }
             }
             K2T_DECL(n_sym += nb;)
@@ -651,29 +677,39 @@ static size_t etc1s_decode_smem_bytes(uint32_t l1_words, int pipes, uint32_t row
     return (((size_t)l1_words * 4 + 15) & ~(size_t)15) + (size_t)pipes * (sizeof(PipeShared) + etc1s_row_state_bytes(row_cap));
 }
 
-cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, int slices_per_cta, uint32_t max_nbx, int sm_count, cudaStream_t stream)
+constexpr size_t kK2SmemLimit = 224 * 1024;
+
+Etc1sDecodePlan plan_etc1s_decode(uint32_t num_slices, uint32_t max_nbx, int sm_count, uint32_t l1_words_small, uint32_t l1_words_big)
+{
+    Etc1sDecodePlan plan;
+    int pipes = (int)((num_slices + (uint32_t)sm_count - 1u) / (uint32_t)(sm_count > 0 ? sm_count : 1));
+    if (pipes < 1) pipes = 1;
+    if (pipes > 8) pipes = 8;                                 // 512 threads: the tokenizer wants more than 64 registers
+    uint32_t row_cap = (max_nbx + 31u) & ~31u;
+    plan.big_tables = pipes == 1 && etc1s_decode_smem_bytes(l1_words_big, 1, row_cap) <= kK2SmemLimit;
+    const uint32_t l1_words = plan.big_tables ? l1_words_big : l1_words_small;
+    if (etc1s_decode_smem_bytes(l1_words, 1, row_cap) > kK2SmemLimit) row_cap = 0;            // very wide slices: row state in global scratch
+    while (pipes > 1 && etc1s_decode_smem_bytes(l1_words, pipes, row_cap) > kK2SmemLimit) pipes--;
+    plan.pipes = pipes;
+    plan.row_cap = row_cap;
+    return plan;
+}
+
+cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, const Etc1sDecodePlan& plan, cudaStream_t stream)
 {
     if (P.num_slices == 0) return cudaSuccess;
-    const size_t limit = 224 * 1024;
-    const uint32_t l1_words = P.l1_ofs[4];
-    // previous-row state in shared memory when it fits, else in the scratch area
-    uint32_t row_cap = (max_nbx + 31u) & ~31u;
-    if (etc1s_decode_smem_bytes(l1_words, 1, row_cap) > limit) row_cap = 0;
-    // spread the slices over the SMs first; pack pipelines (which share the tables) only when there are more slices than SMs
-    int pipes = slices_per_cta > 0 ? slices_per_cta : (int)((P.num_slices + (uint32_t)sm_count - 1u) / (uint32_t)sm_count);
-    if (pipes > 8) pipes = 8;                                 // 512 threads: the tokenizer wants more than 64 registers
-    while (pipes > 1 && etc1s_decode_smem_bytes(l1_words, pipes, row_cap) > limit) pipes--;
-    if (etc1s_decode_smem_bytes(l1_words, pipes, row_cap) > limit) return cudaErrorInvalidValue;     // the host sizes the tables to fit
+    const size_t smem = etc1s_decode_smem_bytes(P.l1_ofs[4], plan.pipes, plan.row_cap);
+    if (smem > kK2SmemLimit) return cudaErrorInvalidValue;                                     // the host sizes the tables to fit
     static bool configured[16] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 16 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(etc1s_entropy_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
+        cudaError_t e = cudaFuncSetAttribute(etc1s_entropy_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK2SmemLimit);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    const unsigned grid = (P.num_slices + pipes - 1) / pipes;
-    etc1s_entropy_decode_kernel<<<grid, 64 * pipes, etc1s_decode_smem_bytes(l1_words, pipes, row_cap), stream>>>(P, (uint32_t)pipes, row_cap);
+    const unsigned grid = (P.num_slices + plan.pipes - 1) / plan.pipes;
+    etc1s_entropy_decode_kernel<<<grid, 64 * plan.pipes, smem, stream>>>(P, (uint32_t)plan.pipes, plan.row_cap);
     return cudaGetLastError();
 }
 

@@ -137,8 +137,9 @@ int b2bu_etc1s_transcode_slices(b2bu_etc1s* h, int target, uint32_t nbx, uint32_
 int b2bu_etc1s_last_timing(b2bu_etc1s* h, float* entropy_ms, float* gather_ms, float* d2h_ms, uint64_t* blocks);
 
 /* How the four slice Huffman models (huffman.rs:133-184; endpoint predictor, delta endpoint, selector, selector
- * run length) sit in K2's shared memory: width in bits of each first-level table and each model's longest code
- * (codes longer than the first-level width are looked up in the flat table in global memory). */
+ * run length) sat in K2's shared memory during the last call on this handle: width in bits of each first-level table
+ * (a wide set is used when every slice gets an SM of its own, a narrow one for packed batches) and each model's
+ * longest code (codes longer than the first-level width are looked up in the flat table in global memory). */
 int b2bu_etc1s_table_info(b2bu_etc1s* h, uint32_t l1_bits[4], uint32_t max_code_len[4]);
 
 /* ---- file level: src/basis.rs:8-260, src/lib.rs:63-79 ---------------------------------------- */
