@@ -77,6 +77,9 @@ def lib() -> ctypes.CDLL:
     L.b2bu_uastc_transcode.argtypes = [c.c_int, u8p, sz, u8p, sz, u64p]
     L.b2bu_uastc_decode_rgba.argtypes = [u8p, sz, sz, u8p, sz, u64p]
     L.b2bu_uastc_transcode_dev.argtypes = [c.c_int, c.c_void_p, sz, sz, c.c_void_p, sz, c.c_void_p, c.c_void_p]
+    L.b2bu_uastc_transcode_slices_dev.argtypes = [c.c_int, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p, c.c_void_p]
+    L.b2bu_crc16_dev.argtypes = [c.c_void_p, sz, c.c_uint16, c.POINTER(c.c_uint16), c.c_void_p]
+    L.b2bu_etc1s_table_info.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]
     L.b2bu_status_reset_dev.argtypes = [c.c_void_p, c.c_void_p]
     L.b2bu_status_read_dev.argtypes = [c.c_void_p, c.c_void_p, u64p]
     L.b2bu_probe_int_peak.argtypes = [c.POINTER(c.c_double), c.POINTER(c.c_double)]
@@ -169,6 +172,12 @@ def uastc_decode_rgba(data, blocks_per_row: int) -> bytes:
 
 
 # ---- ETC1S: basis_lz::Decoder (src/basis_lz/mod.rs:50-186) --------------------------------------
+
+class SliceDev(ctypes.Structure):
+    """b2bu_slice_dev: one slice of a device buffer for b2bu_uastc_transcode_slices_dev."""
+    _fields_ = [("in_ofs", ctypes.c_uint64), ("out_ofs", ctypes.c_uint64), ("nblocks", ctypes.c_uint64),
+                ("blocks_per_row", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
 
 class Etc1sDecoder:
     """basis_lz::Decoder: ``new`` decodes the codebooks / Huffman models once per file."""

@@ -11,7 +11,7 @@ import sys
 HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libb2bu.so"
-SOURCES = ["uastc_kernels.cu", "etc1s_kernels.cu", "etc1s_host.cu", "basis_file.cu", "capi.cu", "probe.cu"]
+SOURCES = ["uastc_kernels.cu", "etc1s_kernels.cu", "etc1s_host.cu", "basis_file.cu", "capi.cu", "probe.cu", "crc_kernels.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
     "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-fvisibility=hidden", "--use_fast_math=false",

@@ -1,8 +1,10 @@
 // .basis container layer of the C ABI: header / slice-descriptor parsing, CRC-16 checks and the
 // per-format slice loops of the reference's file-level API (src/basis.rs:8-372, :419-572),
-// re-designed around the device: every slice of a file is uploaded once into 256-byte aligned
-// device regions, all slice kernels are enqueued back to back on one stream, and the results
-// come back with one copy per image.  Parsing and CRC stay on the host, as in the reference.
+// re-designed around the device.  Files of kGpuCrcMinBytes and more take the fast path: ONE upload
+// of the whole file, the data CRC-16 computed by the GPU (crc_kernels.cu) while the host parses the
+// slice table, the UASTC slices transcoded in place in that upload -- slices that are contiguous in
+// the file (a mip chain) in one launch -- and ONE copy back.  Small files keep the host CRC (a
+// launch and a sync cost more than a few KB of table lookups).
 #include <cstring>
 #include <vector>
 
@@ -10,6 +12,7 @@
 #include "host_internal.h"
 #include "kernels.h"
 #include "etc1s_host.h"
+#include "crc.h"
 
 namespace b2bu {
 
@@ -54,6 +57,9 @@ static SliceDesc parse_slice_desc(const uint8_t* p)
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// files at least this long are uploaded whole and CRC-checked by the GPU
+constexpr size_t kGpuCrcMinBytes = 256 * 1024;
+
 }  // namespace b2bu
 
 using namespace b2bu;
@@ -76,6 +82,15 @@ int b2bu_read_header(const uint8_t* buf, size_t len, b2bu_header* h)
     return B2BU_OK;
 }
 
+// the reference checks the data CRC first (basis.rs:9-13); whatever the host finds wrong afterwards must not hide a CRC error
+static int finish_device_crc(DeviceCtx* c, cudaStream_t s, uint64_t crc_len, uint32_t expected, int body_status)
+{
+    CK(cudaMemcpyAsync(c->h_crc, c->d_crc, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (crc16_finish(*c->h_crc, crc_len, 0) != expected) return B2BU_ERR_DATA_CRC;
+    return body_status;
+}
+
 int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header, b2bu_image* images, uint32_t max_images,
                  uint32_t* num_images, uint8_t* out, uint64_t out_cap, uint64_t* out_needed)
 {
@@ -86,7 +101,32 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
     int st = b2bu_read_header(buf, len, &h);
     if (st) return st;
     if (header) *header = h;
-    if (crc16_host(buf + 77, len - 77, 0) != h.data_crc16) return B2BU_ERR_DATA_CRC;   // basis.rs:338-341
+    // basis.rs:338-341.  Large files: the transcoding call computes the CRC on the device; a pure sizing call (out == NULL)
+    // of a large file leaves the data CRC to the transcoding call that follows it.
+    const bool big = len >= kGpuCrcMinBytes;
+    const bool gpu_crc = big && out != nullptr;
+    if (!big && crc16_host(buf + 77, len - 77, 0) != h.data_crc16) return B2BU_ERR_DATA_CRC;
+
+    DeviceCtx* c = nullptr;
+    std::unique_lock<std::mutex> lk;
+    uint8_t* d_file = nullptr;                     // device copy of the file, shifted so that file offset 0 mod 16 == device address 0 mod 16
+    cudaStream_t s0 = nullptr;
+    if (gpu_crc) {
+        if ((st = get_ctx(&c))) return st;
+        lk = std::unique_lock<std::mutex>(c->run_mu);
+        if ((st = ensure(&c->d_file, &c->file_cap, len + 16))) return st;
+        // shift the upload so that the first slice (and with it every slice that shares its 16-byte phase) is 16-byte aligned
+        uint32_t phase = 0;
+        if ((uint64_t)h.slice_desc_file_ofs + 23 <= len && h.total_slices) phase = parse_slice_desc(buf + h.slice_desc_file_ofs).file_ofs & 15u;
+        d_file = static_cast<uint8_t*>(c->d_file) + ((16u - phase) & 15u);
+        s0 = c->streams[0];
+        CK(cudaMemcpyAsync(d_file, buf, len, cudaMemcpyHostToDevice, s0));
+        CK(cudaMemsetAsync(c->d_crc, 0, sizeof(uint32_t), s0));
+        CK(launch_crc16_dev(d_file + 77, len - 77, c->d_crc, c->sm_count, s0));
+        count_launch(1);
+    }
+    // everything below is the body after the CRC check; with the device CRC in flight its status is held back until the CRC is known
+    auto body = [&]() -> int {
     // basis.rs:343-362 read_slice_descs
     std::vector<SliceDesc> descs(h.total_slices);
     for (uint32_t i = 0; i < h.total_slices; i++) {
@@ -143,12 +183,34 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
         for (uint32_t i = 0; i < nimg; i++) memcpy(out + plan[i].offset, buf + descs[i].file_ofs, descs[i].file_size);
         return B2BU_OK;
     }
-    if (etc1s) return etc1s_read_file(target, buf, len, h, descs.data(), plan.data(), nimg, pair, out);
+    if (etc1s) return etc1s_read_file(target, buf, len, h, descs.data(), plan.data(), nimg, pair, out, d_file);
 
-    // ---- UASTC file: upload every slice once, launch all, copy back -------------------------
-    DeviceCtx* c;
-    if ((st = get_ctx(&c))) return st;
-    std::lock_guard<std::mutex> lk(c->run_mu);
+    // ---- UASTC file ------------------------------------------------------------------------------
+    int st2;
+    if (!c) {
+        if ((st2 = get_ctx(&c))) return st2;
+        lk = std::unique_lock<std::mutex>(c->run_mu);
+        s0 = c->streams[0];
+    }
+    // fast path: the slices are transcoded where they lie in the uploaded file (their offsets must share the upload's
+    // 16-byte phase; the encoder writes UASTC slices back to back, so they do) into the host layout of the result
+    bool in_place = d_file != nullptr;
+    for (uint32_t i = 0; i < nimg && in_place; i++)
+        in_place = descs[i].file_size == 0 || ((reinterpret_cast<uintptr_t>(d_file) + descs[i].file_ofs) & 15) == 0;
+    CK(cudaMemsetAsync(c->d_err, 0xFF, sizeof(unsigned long long), s0));
+    if (in_place) {
+        if ((st2 = ensure(&c->d_out[0], &c->out_cap[0], total))) return st2;
+        std::vector<b2bu_slice_dev> sl(nimg);
+        const uint8_t* abase = static_cast<const uint8_t*>(c->d_file);              // 256-byte aligned
+        for (uint32_t i = 0; i < nimg; i++)
+            sl[i] = {descs[i].file_size ? (uint64_t)(d_file + descs[i].file_ofs - abase) : 0u, plan[i].offset, descs[i].file_size / 16, descs[i].num_blocks_x, 0u};
+        if ((st2 = b2bu_uastc_transcode_slices_dev(target, abase, c->d_out[0], sl.data(), nimg, c->d_err, s0))) return st2;
+        CK(cudaMemcpyAsync(out, c->d_out[0], total, cudaMemcpyDeviceToHost, s0));
+        CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s0));
+        CK(cudaStreamSynchronize(s0));
+        return decode_status_word(*c->h_err, nullptr);
+    }
+    // general path: every slice uploaded on its own into a 256-byte aligned region
     size_t in_total = 0;
     std::vector<size_t> in_ofs(nimg), out_ofs(nimg);
     size_t out_total = 0;
@@ -156,12 +218,11 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
         in_ofs[i] = in_total; in_total += align_up(descs[i].file_size, 256);
         out_ofs[i] = out_total; out_total += align_up(plan[i].nbytes, 256);
     }
-    if ((st = ensure(&c->d_in[0], &c->in_cap[0], in_total))) return st;
-    if ((st = ensure(&c->d_out[0], &c->out_cap[0], out_total))) return st;
-    cudaStream_t s0 = c->streams[0], s1 = c->streams[1];
+    if ((st2 = ensure(&c->d_in[0], &c->in_cap[0], in_total))) return st2;
+    if ((st2 = ensure(&c->d_out[0], &c->out_cap[0], out_total))) return st2;
+    cudaStream_t s1 = c->streams[1];
     uint8_t* d_in = static_cast<uint8_t*>(c->d_in[0]);
     uint8_t* d_out = static_cast<uint8_t*>(c->d_out[0]);
-    CK(cudaMemsetAsync(c->d_err, 0xFF, sizeof(unsigned long long), s0));
     // one status word per file would lose which slice failed first in file order, so slices are
     // given disjoint index ranges: index_base = blocks of all earlier slices
     uint64_t base = 0;
@@ -183,6 +244,10 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
     for (uint32_t i = 0; i < nimg; i++) cudaEventDestroy(done[i]);
     CK(cudaMemcpy(c->h_err, c->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return decode_status_word(*c->h_err, nullptr);
+    };
+    st = body();
+    if (gpu_crc) return finish_device_crc(c, s0, len - 77, h.data_crc16, st);
+    return st;
 }
 
 }  // extern "C"

@@ -13,6 +13,7 @@
 #include "../../include/b2bu.h"
 #include "host_internal.h"
 #include "kernels.h"
+#include "crc.h"
 
 namespace b2bu {
 
@@ -52,6 +53,8 @@ int get_ctx(DeviceCtx** out)
         }
         CK(cudaMalloc(&c.d_err, sizeof(unsigned long long)));
         CK(cudaMallocHost(&c.h_err, sizeof(unsigned long long)));
+        CK(cudaMalloc(&c.d_crc, sizeof(uint32_t)));
+        CK(cudaMallocHost(&c.h_crc, sizeof(uint32_t)));
         c.ready = true;
     }
     *out = &c;
@@ -246,6 +249,71 @@ int b2bu_uastc_transcode_dev(int target, const void* d_blocks, size_t nbytes, si
     CK(launch_uastc_transcode(target, d_blocks, d_out, n, (uint32_t)(blocks_per_row ? blocks_per_row : 1), 0,
                               reinterpret_cast<unsigned long long*>(d_status), c->sm_count, reinterpret_cast<cudaStream_t>(stream)));
     count_launch(1);
+    return B2BU_OK;
+}
+
+int b2bu_uastc_transcode_slices_dev(int target, const void* d_blocks, void* d_out, const b2bu_slice_dev* slices, uint32_t num_slices,
+                                    void* d_status, void* stream)
+{
+    if (target < B2BU_RGBA || target > B2BU_ETC2) return B2BU_ERR_ARGUMENT;
+    if (num_slices == 0) return B2BU_OK;
+    if (!d_blocks || !d_out || !slices || !d_status) return B2BU_ERR_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(d_blocks) | reinterpret_cast<uintptr_t>(d_out)) & 15) return B2BU_ERR_ARGUMENT;
+    const uint64_t ob = b2bu_block_bytes(target);
+    for (uint32_t i = 0; i < num_slices; i++) {
+        const b2bu_slice_dev& s = slices[i];
+        if ((s.in_ofs & 15) || (s.out_ofs & (target == B2BU_ETC1 ? 7 : 15))) return B2BU_ERR_ARGUMENT;
+        if (target == B2BU_RGBA && s.nblocks && (s.blocks_per_row == 0 || s.nblocks % s.blocks_per_row != 0)) return B2BU_ERR_ARGUMENT;
+    }
+    DeviceCtx* c;
+    int st = get_ctx(&c);
+    if (st) return st;
+    const uint8_t* in = static_cast<const uint8_t*>(d_blocks);
+    uint8_t* out = static_cast<uint8_t*>(d_out);
+    uint64_t base = 0;
+    for (uint32_t i = 0; i < num_slices;) {
+        // a run of slices that is one contiguous block array on both sides (RGBA output depends on the slice shape: no merging)
+        uint64_t n = slices[i].nblocks;
+        uint32_t j = i + 1;
+        if (target != B2BU_RGBA)
+            while (j < num_slices && slices[j].in_ofs == slices[i].in_ofs + n * 16 && slices[j].out_ofs == slices[i].out_ofs + n * ob) n += slices[j++].nblocks;
+        if (n) {
+            uint64_t skip = 0;
+            if (target == B2BU_ETC1 && (slices[i].out_ofs & 15)) {
+                // 8-byte blocks: a run that starts in the middle of a 16-byte line gives its first block to the small kernel so
+                // that the tile kernel's bulk stores stay 16-byte aligned
+                skip = 1;
+                CK(launch_uastc_transcode(target, in + slices[i].in_ofs, out + slices[i].out_ofs, 1, 1u, base, reinterpret_cast<unsigned long long*>(d_status),
+                                          c->sm_count, reinterpret_cast<cudaStream_t>(stream)));
+                count_launch(1);
+            }
+            if (n > skip) {
+                CK(launch_uastc_transcode(target, in + slices[i].in_ofs + skip * 16, out + slices[i].out_ofs + skip * ob, n - skip,
+                                          slices[i].blocks_per_row ? slices[i].blocks_per_row : 1u, base + skip,
+                                          reinterpret_cast<unsigned long long*>(d_status), c->sm_count, reinterpret_cast<cudaStream_t>(stream)));
+                count_launch(1);
+            }
+        }
+        base += n;
+        i = j;
+    }
+    return B2BU_OK;
+}
+
+int b2bu_crc16_dev(const void* d_data, size_t len, uint16_t crc, uint16_t* result, void* stream)
+{
+    if (!result || (len && !d_data)) return B2BU_ERR_ARGUMENT;
+    DeviceCtx* c;
+    int st = get_ctx(&c);
+    if (st) return st;
+    std::lock_guard<std::mutex> lk(c->run_mu);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    CK(cudaMemsetAsync(c->d_crc, 0, sizeof(uint32_t), s));
+    CK(launch_crc16_dev(d_data, len, c->d_crc, c->sm_count, s));
+    count_launch(len ? 1 : 0);
+    CK(cudaMemcpyAsync(c->h_crc, c->d_crc, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *result = crc16_finish(*c->h_crc, len, crc);
     return B2BU_OK;
 }
 

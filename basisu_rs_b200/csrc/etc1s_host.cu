@@ -226,7 +226,7 @@ static int upload(uint32_t** dst, const std::vector<uint32_t>& v)
     return B2BU_OK;
 }
 
-struct SliceReq { const uint8_t* data; uint64_t len; uint32_t nbx, nby; };
+struct SliceReq { const uint8_t* data; uint64_t len; uint32_t nbx, nby; const uint8_t* d_data; };   // d_data: the same bytes on the device, or null
 struct ImageReq { int rgb_slice, alpha_slice; uint64_t out_ofs; };      // indices into the slice list; alpha_slice = -1 if none
 
 // Decodes `slices` with K2 and emits one output per image with K3.  target: B2BU_ETC1 (images = slices)
@@ -260,7 +260,10 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
     if ((st = ensure(&h->d_status, &h->status_cap, ns * 4))) return st;
     cudaStream_t s = c->streams[0];
     for (size_t i = 0; i < ns; i++)
-        if (slices[i].len) CK(cudaMemcpyAsync(static_cast<uint8_t*>(h->d_data) + jobs[i].data_ofs, slices[i].data, slices[i].len, cudaMemcpyHostToDevice, s));
+        if (slices[i].len) {
+            if (slices[i].d_data) CK(cudaMemcpyAsync(static_cast<uint8_t*>(h->d_data) + jobs[i].data_ofs, slices[i].d_data, slices[i].len, cudaMemcpyDeviceToDevice, s));
+            else CK(cudaMemcpyAsync(static_cast<uint8_t*>(h->d_data) + jobs[i].data_ofs, slices[i].data, slices[i].len, cudaMemcpyHostToDevice, s));
+        }
     CK(cudaMemcpyAsync(h->d_jobs, jobs.data(), ns * sizeof(Etc1sSliceJob), cudaMemcpyHostToDevice, s));
 
     for (int i = 0; i < 4; i++) if (!h->ev[i]) CK(cudaEventCreate(&h->ev[i]));
@@ -398,7 +401,7 @@ static int etc1s_open_impl(uint32_t endpoint_count, uint32_t selector_count, con
 }
 
 int etc1s_read_file(int target, const uint8_t* buf, size_t len, const b2bu_header& hd, const SliceDesc* descs, const b2bu_image* plan,
-                    uint32_t nimg, bool pair, uint8_t* out)
+                    uint32_t nimg, bool pair, uint8_t* out, const uint8_t* d_file)
 {
     // basis.rs:262-300 make_basis_lz_decoder: sections are slices of the file (out of range => the reference panics)
     if ((uint64_t)hd.endpoint_cb_file_ofs + hd.endpoint_cb_file_size > len || (uint64_t)hd.selector_cb_file_ofs + hd.selector_cb_file_size > len ||
@@ -416,12 +419,12 @@ int etc1s_read_file(int target, const uint8_t* buf, size_t len, const b2bu_heade
         const SliceDesc& s = descs[pair ? 2 * i : i];
         ImageReq im;
         im.rgb_slice = (int)slices.size();
-        slices.push_back({buf + s.file_ofs, s.file_size, s.num_blocks_x, s.num_blocks_y});
+        slices.push_back({buf + s.file_ofs, s.file_size, s.num_blocks_x, s.num_blocks_y, d_file ? d_file + s.file_ofs : nullptr});
         im.alpha_slice = -1;
         if (pair) {
             const SliceDesc& a = descs[2 * i + 1];
             im.alpha_slice = (int)slices.size();
-            slices.push_back({buf + a.file_ofs, a.file_size, a.num_blocks_x, a.num_blocks_y});
+            slices.push_back({buf + a.file_ofs, a.file_size, a.num_blocks_x, a.num_blocks_y, d_file ? d_file + a.file_ofs : nullptr});
         }
         im.out_ofs = plan[i].offset;
         images.push_back(im);
@@ -485,7 +488,7 @@ int b2bu_etc1s_transcode_slices(b2bu_etc1s* h, int target, uint32_t nbx, uint32_
     std::vector<ImageReq> images(num_slices);
     for (uint32_t i = 0; i < num_slices; i++) {
         if (slice_ofs[i] + slice_len[i] > data_len) return B2BU_ERR_RANGE;
-        slices[i] = {data + slice_ofs[i], slice_len[i], nbx, nby};
+        slices[i] = {data + slice_ofs[i], slice_len[i], nbx, nby, nullptr};
         images[i] = {(int)i, -1, per * i};
     }
     return etc1s_run(h, target, slices, images, out, per * num_slices);
@@ -504,8 +507,8 @@ int b2bu_etc1s_decode_to_rgba(b2bu_etc1s* h, uint32_t nbx, uint32_t nby, const u
     const uint64_t total = (uint64_t)nbx * nby * 64;
     if (out_bytes < total) return B2BU_ERR_ARGUMENT;
     std::vector<SliceReq> slices;
-    slices.push_back({rgb_slice, rgb_len, nbx, nby});
-    if (alpha_slice) slices.push_back({alpha_slice, alpha_len, nbx, nby});
+    slices.push_back({rgb_slice, rgb_len, nbx, nby, nullptr});
+    if (alpha_slice) slices.push_back({alpha_slice, alpha_len, nbx, nby, nullptr});
     std::vector<ImageReq> images(1);
     images[0] = {0, alpha_slice ? 1 : -1, 0};
     return etc1s_run(h, B2BU_RGBA, slices, images, out, total);

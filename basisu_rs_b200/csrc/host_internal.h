@@ -30,6 +30,10 @@ struct DeviceCtx {
     cudaEvent_t ev_h2d[kStreams] = {}, ev_kernel[kStreams] = {}, ev_d2h[kStreams] = {};   // per buffer slot
     unsigned long long* d_err = nullptr;          // one status word, atomicMin'ed by every launch of a call
     unsigned long long* h_err = nullptr;          // pinned
+    void* d_file = nullptr;                       // whole .basis file of the current b2bu_read_to call (device CRC + in-place slices)
+    size_t file_cap = 0;
+    uint32_t* d_crc = nullptr;                    // CRC partial-sum word
+    uint32_t* h_crc = nullptr;                    // pinned
 };
 
 // basis.rs:520-535

@@ -102,6 +102,19 @@ int b2bu_uastc_decode_rgba(const uint8_t* blocks, size_t nbytes, size_t blocks_p
  * then read it back with b2bu_status_read_dev (synchronises the stream). */
 int b2bu_uastc_transcode_dev(int target, const void* d_blocks, size_t nbytes, size_t blocks_per_row, void* d_out,
                              size_t out_bytes, void* d_status, void* stream);
+/* Several slices of one device buffer in one call -- the mip chain of a texture, the images of a file
+ * (basis.rs:145-260 loop over the slice descriptors and call Decoder::transcode once per slice).  in_ofs /
+ * out_ofs are byte offsets from d_blocks / d_out (multiples of 16; out_ofs of B2BU_ETC1: of 8, so that
+ * slices with odd block counts can be packed back to back); blocks_per_row is only used by
+ * B2BU_RGBA.  For the other targets, slices that follow each other without a gap in both buffers are
+ * merged into ONE kernel launch: a full mip chain is a single launch instead of 14.  In d_status, block
+ * indices count through the slices in array order. */
+typedef struct b2bu_slice_dev {
+    uint64_t in_ofs, out_ofs, nblocks;
+    uint32_t blocks_per_row, reserved;
+} b2bu_slice_dev;
+int b2bu_uastc_transcode_slices_dev(int target, const void* d_blocks, void* d_out, const b2bu_slice_dev* slices,
+                                    uint32_t num_slices, void* d_status, void* stream);
 int b2bu_status_reset_dev(void* d_status, void* stream);
 int b2bu_status_read_dev(const void* d_status, void* stream, uint64_t* first_bad_block);
 /* Measurement aid: thread-level integer instruction throughput of the current device in Tops/s, for a stream of alu-pipe
@@ -160,6 +173,11 @@ typedef struct b2bu_image {        /* lib.rs:63-68 Image<u8> + where its data si
 int b2bu_read_header(const uint8_t* buf, size_t len, b2bu_header* header);
 /* basis.rs:364-372 crc16 */
 uint16_t b2bu_crc16(const uint8_t* data, size_t len, uint16_t crc);
+/* The same CRC over len bytes of DEVICE memory (any alignment), computed by the GPU: the register update is
+ * GF(2)-linear, so 16 KiB chunks are reduced independently and combined with powers of x.  Synchronises the
+ * stream.  b2bu_read_to uses this path for files of 256 KiB and more (one upload of the whole file, CRC and
+ * transcode kernels back to back), so that the file-level API is not bound by a single-core CRC loop. */
+int b2bu_crc16_dev(const void* d_data, size_t len, uint16_t crc, uint16_t* result, void* stream);
 
 /* basis.rs:8,92,145,175,204,233 read_to_{rgba,etc1,etc2,uastc,astc,bc7}.
  * Call with out == NULL to size: fills header, images[0..min(n,max_images)) (offset/nbytes/w/h/

@@ -78,6 +78,29 @@ def test_file_level_read_to_rgba_and_etc1(gpu_lib, oracle):
         assert ei_.value.status == 14
 
 
+def test_file_level_large_file_device_crc_path(gpu_lib, oracle):
+    """An ETC1S file above the 256 KiB threshold: one upload, CRC-16 on the GPU, slices gathered device-to-device."""
+    orc = bind(oracle)
+    nbx, nby, ncb = 200, 160, 4000
+    _, _, ei, si, enc = make_case(orc, nbx, nby, 6, ncb, seed=29)
+    f = etc1s_file(enc, nbx, nby, ncb, alpha_pairs=True)
+    assert len(f) > 256 * 1024
+    e, want = oracle_read_to(orc, 0, f)
+    assert e == 0
+    header, images = gpu_lib.read_to_rgba(f)
+    assert [(im.w, im.h, im.stride, im.data) for im in images] == want
+    e, want = oracle_read_to(orc, 3, f)
+    assert [(im.w, im.h, im.stride, im.data) for im in gpu_lib.read_to_etc1(f)] == want
+    g = bytearray(f); g[len(g) - 1000] ^= 0x11
+    with pytest.raises(gpu_lib.BasisuError) as ei_:
+        gpu_lib.read_to_etc1(bytes(g))
+    assert str(ei_.value) == "Data CRC16 failed"
+    g = bytearray(f); g[100] ^= 0x11                      # inside the slice descriptors / codebooks: the CRC error still wins
+    with pytest.raises(gpu_lib.BasisuError) as ei_:
+        gpu_lib.read_to_rgba(bytes(g))
+    assert str(ei_.value) == "Data CRC16 failed"
+
+
 def test_corrupt_streams_report_like_the_oracle(gpu_lib, oracle):
     orc = bind(oracle)
     nbx, nby, ncb = 40, 30, 500
