@@ -47,6 +47,23 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// wait of a role that has nothing else to do for microseconds (the DMA lane waiting for a tile to be finished): polls with
+// a sleep in between, so that the waiting warp does not take issue slots from the warps it is waiting for
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t sleep_ns)
+{
+    uint32_t ok;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        asm volatile("nanosleep.u32 %0;" ::"r"(sleep_ns));
+    }
+}
+
 // one bounded try_wait: returns false when the phase has not flipped within the suspend-time hint
 __device__ __forceinline__ bool mbar_try_wait_once(uint64_t* bar, uint32_t parity)
 {

@@ -132,6 +132,16 @@ __device__ unsigned long long g_trace[160][64];
 #define TRACE_ADD(slot, v) do { } while (0)
 #endif
 
+// the DMA lane's waits for a finished tile: sleeping polls (see mbar_wait_backoff); B2BU_DMA_SLEEP_NS = 0 spins
+#ifndef B2BU_DMA_SLEEP_NS
+#define B2BU_DMA_SLEEP_NS 200
+#endif
+#if B2BU_DMA_SLEEP_NS > 0
+#define B2BU_DMA_WAIT(bar, parity) mbar_wait_backoff((bar), (parity), B2BU_DMA_SLEEP_NS)
+#else
+#define B2BU_DMA_WAIT(bar, parity) mbar_wait((bar), (parity))
+#endif
+
 template <int TARGET> struct PipeCfg {
     static constexpr int OB = TARGET == TGT_RGBA ? 64 : TARGET == TGT_ETC1 ? 8 : 16;
     static constexpr bool IN_PLACE = OB == 16;
@@ -254,7 +264,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
         for (uint32_t k = 0; k < ntiles; k++) {
             const uint32_t s = k & 1u, u = k >> 1;
             if (k >= 2) {                                      // slot reuse: tile k-2 must be finished and stored
-                mbar_wait(&bar_done[s], (u - 1u) & 1u);
+                B2BU_DMA_WAIT(&bar_done[s], (u - 1u) & 1u);
                 store_tile(k - 2);
                 tma_store_wait_read();
             }
@@ -264,7 +274,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
             do { if (k < 6) TRACE(k * 6 + 0); } while (0);
         }
         for (uint32_t k = ntiles >= 2 ? ntiles - 2 : 0; k < ntiles; k++) {
-            mbar_wait(&bar_done[k & 1u], (k >> 1) & 1u);
+            B2BU_DMA_WAIT(&bar_done[k & 1u], (k >> 1) & 1u);
             store_tile(k);
         }
         tma_store_wait_all();

@@ -2,7 +2,7 @@
 # Runs bench.py --all-targets over every tuning variant basisu_rs_b200/libv_*.so (plus the default build).
 for lib in basisu_rs_b200/libb2bu.so basisu_rs_b200/libv_*.so; do
   name=$(basename $lib .so)
-  B2BU_LIBRARY=$PWD/$lib timeout 200 python bench.py --all-targets --no-cpu-baseline --steps 50 --e2e-steps 2 > gpurun_out/tune_$name.json 2> gpurun_out/tune_$name.err
+  B2BU_LIBRARY=$PWD/$lib timeout 200 python bench.py --all-targets --no-cpu-baseline --steps 50 --e2e-steps 2 --configs none > gpurun_out/tune_$name.json 2> gpurun_out/tune_$name.err
   python - <<PY
 import json
 try:
