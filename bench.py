@@ -35,6 +35,25 @@ ALGO_BYTES = {0: 80, 1: 32, 2: 32, 3: 24, 4: 32}
 INT_OPS = {0: 400, 1: 300, 2: 550, 3: 800, 4: 1300}        # algorithmic integer ops per block
 
 
+
+# The contract is ONE JSON line on stdout.  Libraries under us write there too (NCCL prints its version banner to
+# stdout), so everything else is routed to stderr: fd 1 is pointed at fd 2 for the whole run and the line goes to the
+# saved descriptor.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
 def make_payload(kind: str, nblocks: int, seed: int = 0) -> np.ndarray:
     """Synthetic UASTC payloads of SURVEY.md section 8d, built from the reference's 608 golden input
     blocks (tests/golden/uastc_kat.bin): kat-coherent = tiled in file order (runs of 32 same-mode
@@ -173,7 +192,7 @@ def run_reference_arm(args, rank, world):
         "gpu_launches": 0,
         "note": "reference (Rust) cannot be built here: no rustc/cargo; this is the C restatement pinned on the reference's 3,040 KATs",
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 
@@ -445,6 +464,7 @@ def main():
     ap.add_argument("--c4-blocks", type=int, default=1024, help="ETC1S slice edge in blocks (1024 = 4096x4096 texels)")
     ap.add_argument("--c4-slices", type=int, default=64)
     args = ap.parse_args()
+    capture_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -635,7 +655,7 @@ def main():
             line["extra"] = extra
         if cfgs:
             line["configs"] = cfgs
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
