@@ -26,7 +26,7 @@ __all__ = [
     "RGBA", "ASTC", "BC7", "ETC1", "ETC2", "UASTC",
 ]
 
-RGBA, ASTC, BC7, ETC1, ETC2, UASTC = 0, 1, 2, 3, 4, 5
+RGBA, ASTC, BC7, ETC1, ETC2, UASTC, BC1 = 0, 1, 2, 3, 4, 5, 6
 BLOCK_BYTES = {RGBA: 64, ASTC: 16, BC7: 16, ETC1: 8, ETC2: 16, UASTC: 16}
 
 _HERE = pathlib.Path(__file__).resolve().parent
@@ -87,6 +87,7 @@ def lib() -> ctypes.CDLL:
     L.b2bu_etc1s_open.argtypes = [c.c_uint32, c.c_uint32, u8p, sz, u8p, sz, u8p, sz, c.c_int, c.POINTER(c.c_void_p)]
     L.b2bu_etc1s_close.argtypes = [c.c_void_p]
     L.b2bu_etc1s_transcode_to_etc1.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, u8p, sz, u8p, sz]
+    L.b2bu_etc1s_transcode_to_bc1.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, u8p, sz, u8p, sz]
     L.b2bu_etc1s_decode_to_rgba.argtypes = [c.c_void_p, c.c_uint32, c.c_uint32, u8p, sz, u8p, sz, u8p, sz]
     L.b2bu_etc1s_transcode_slices.argtypes = [c.c_void_p, c.c_int, c.c_uint32, c.c_uint32, u8p, sz, u64p, u64p, c.c_uint32, u8p, sz]
     L.b2bu_etc1s_last_timing.argtypes = [c.c_void_p, c.POINTER(c.c_float), c.POINTER(c.c_float), c.POINTER(c.c_float), u64p]
@@ -201,6 +202,14 @@ class Etc1sDecoder:
         out_len = num_blocks_x * num_blocks_y * 8
         out = (ctypes.c_uint8 * max(out_len, 1))()
         _check(lib().b2bu_etc1s_transcode_to_etc1(self._h, num_blocks_x, num_blocks_y, src, n, out, out_len))
+        return bytes(out)[:out_len]
+
+    def transcode_to_bc1(self, num_blocks_x, num_blocks_y, block_data) -> bytes:
+        """EXTENSION (the reference has no BC1): see b2bu_etc1s_transcode_to_bc1 in include/b2bu.h."""
+        src, n = _buf(block_data)
+        out_len = num_blocks_x * num_blocks_y * 8
+        out = (ctypes.c_uint8 * max(out_len, 1))()
+        _check(lib().b2bu_etc1s_transcode_to_bc1(self._h, num_blocks_x, num_blocks_y, src, n, out, out_len))
         return bytes(out)[:out_len]
 
     def decode_to_rgba(self, num_blocks_x, num_blocks_y, rgb_data, alpha_data=None) -> bytes:

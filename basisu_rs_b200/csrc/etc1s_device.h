@@ -51,6 +51,8 @@ Etc1sDecodePlan plan_etc1s_decode(uint32_t num_slices, uint32_t max_nbx, int sm_
 cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, const Etc1sDecodePlan& plan, cudaStream_t stream);
 cudaError_t launch_etc1s_gather_etc1(const uint32_t* idx, uint64_t nblocks, const uint32_t* endpoints, const uint32_t* sel_etc1, void* out,
                                      int sm_count, cudaStream_t stream);
+cudaError_t launch_etc1s_gather_bc1(const uint32_t* idx, uint64_t nblocks, const uint32_t* endpoints, const uint32_t* sel_plain, void* out,
+                                    int sm_count, cudaStream_t stream);
 cudaError_t launch_etc1s_gather_rgba(const uint32_t* idx_rgb, const uint32_t* idx_alpha, uint32_t nbx, uint64_t nblocks, const uint32_t* endpoints,
                                      const uint32_t* sel_plain, void* out, int sm_count, cudaStream_t stream);
 

@@ -292,6 +292,9 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
         // images are the slices in order and ETC1 output does not depend on the slice shape: one gather over everything
         CK(launch_etc1s_gather_etc1(idx, blocks_total, h->d_endpoints, h->d_sel_etc1, h->d_out, c->sm_count, s));
         count_launch(1);
+    } else if (target == B2BU_BC1) {
+        CK(launch_etc1s_gather_bc1(idx, blocks_total, h->d_endpoints, h->d_sel_plain, h->d_out, c->sm_count, s));
+        count_launch(1);
     } else {
         for (const ImageReq& im : images) {
             const Etc1sSliceJob& j = jobs[im.rgb_slice];
@@ -481,8 +484,9 @@ int b2bu_etc1s_table_info(b2bu_etc1s* h, uint32_t l1_bits[4], uint32_t max_code_
 int b2bu_etc1s_transcode_slices(b2bu_etc1s* h, int target, uint32_t nbx, uint32_t nby, const uint8_t* data, size_t data_len,
                                 const uint64_t* slice_ofs, const uint64_t* slice_len, uint32_t num_slices, uint8_t* out, size_t out_bytes)
 {
-    if (!h || (target != B2BU_ETC1 && target != B2BU_RGBA) || (num_slices && (!data || !slice_ofs || !slice_len || !out))) return B2BU_ERR_ARGUMENT;
-    const uint64_t per = (uint64_t)nbx * nby * (target == B2BU_ETC1 ? 8 : 64);
+    if (!h || (target != B2BU_ETC1 && target != B2BU_RGBA && target != B2BU_BC1) || (num_slices && (!data || !slice_ofs || !slice_len || !out)))
+        return B2BU_ERR_ARGUMENT;
+    const uint64_t per = (uint64_t)nbx * nby * (target == B2BU_RGBA ? 64 : 8);
     if (out_bytes < per * num_slices) return B2BU_ERR_ARGUMENT;
     std::vector<SliceReq> slices(num_slices);
     std::vector<ImageReq> images(num_slices);
@@ -498,6 +502,12 @@ int b2bu_etc1s_transcode_to_etc1(b2bu_etc1s* h, uint32_t nbx, uint32_t nby, cons
 {
     const uint64_t ofs = 0, len = slice_len;
     return b2bu_etc1s_transcode_slices(h, B2BU_ETC1, nbx, nby, slice, slice_len, &ofs, &len, 1, out, out_bytes);
+}
+
+int b2bu_etc1s_transcode_to_bc1(b2bu_etc1s* h, uint32_t nbx, uint32_t nby, const uint8_t* slice, size_t slice_len, uint8_t* out, size_t out_bytes)
+{
+    const uint64_t ofs = 0, len = slice_len;
+    return b2bu_etc1s_transcode_slices(h, B2BU_BC1, nbx, nby, slice, slice_len, &ofs, &len, 1, out, out_bytes);
 }
 
 int b2bu_etc1s_decode_to_rgba(b2bu_etc1s* h, uint32_t nbx, uint32_t nby, const uint8_t* rgb_slice, size_t rgb_len, const uint8_t* alpha_slice,

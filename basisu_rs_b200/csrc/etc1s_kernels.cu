@@ -618,6 +618,70 @@ __global__ void __launch_bounds__(256) etc1s_gather_etc1_kernel(const uint32_t* 
     }
 }
 
+// K3c (EXTENSION, not in the reference -- the definition is oracle/basisu_oracle_etc1s.inc etc1s_emit_bc1): ETC1S -> BC1.
+// The selector word (one byte per row, 2 bits per x) already has BC1's index layout, so the per-texel step is a 4-entry
+// remap of 2-bit fields done on the whole word at once.
+__global__ void __launch_bounds__(256) etc1s_gather_bc1_kernel(const uint32_t* __restrict__ idx, uint64_t nblocks,
+                                                               const uint32_t* __restrict__ endpoints, const uint32_t* __restrict__ sel_plain,
+                                                               uint2* __restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nblocks; i += stride) {
+        const uint32_t v = idx[i];
+        const uint32_t e = __ldg(endpoints + (v & 0xFFFFu));                       // inten | r5 << 8 | g5 << 16 | b5 << 24
+        const uint32_t rows = __ldg(sel_plain + (v >> 16));
+        const uint32_t inten = e & 7u;
+        int C[4][3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const uint32_t c5 = (e >> (8 + 8 * c)) & 0xFFu;
+            const int base = (int)(((c5 << 3) | (c5 >> 2)) & 0xFFu);               // etc.rs:396-406
+#pragma unroll
+            for (int k = 0; k < 4; k++) { int t = base + __ldg(&kEtc1Mod[inten * 4 + k]); C[k][c] = t < 0 ? 0 : t > 255 ? 255 : t; }
+        }
+        // fields equal to k, as a 01 pattern per 2-bit field
+        const uint32_t L = rows & 0x55555555u, H = (rows >> 1) & 0x55555555u;
+        const uint32_t eq[4] = {~H & ~L & 0x55555555u, ~H & L, H & ~L, H & L};
+        const int lo = eq[0] ? 0 : eq[1] ? 1 : eq[2] ? 2 : 3;
+        const int hi = eq[3] ? 3 : eq[2] ? 2 : eq[1] ? 1 : 0;
+        uint32_t w[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const int k = t ? hi : lo;
+            int r = C[0][0], g = C[0][1], b = C[0][2];
+#pragma unroll
+            for (int q = 1; q < 4; q++) if (k == q) { r = C[q][0]; g = C[q][1]; b = C[q][2]; }
+            w[t] = (((uint32_t)r * 31u + 127u) / 255u) << 11 | (((uint32_t)g * 63u + 127u) / 255u) << 5 | (((uint32_t)b * 31u + 127u) / 255u);
+        }
+        const uint32_t c0 = w[0] > w[1] ? w[0] : w[1], c1 = w[0] > w[1] ? w[1] : w[0];
+        uint32_t bits = 0u;
+        if (c0 != c1) {
+            int pal[4][3];
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const uint32_t u = t ? c1 : c0, r5 = u >> 11, g6 = (u >> 5) & 63u, b5 = u & 31u;
+                pal[t][0] = (int)((r5 << 3) | (r5 >> 2)); pal[t][1] = (int)((g6 << 2) | (g6 >> 4)); pal[t][2] = (int)((b5 << 3) | (b5 >> 2));
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) { pal[2][c] = (2 * pal[0][c] + pal[1][c]) / 3; pal[3][c] = (pal[0][c] + 2 * pal[1][c]) / 3; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int best = 0x7fffffff;
+                uint32_t m = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    int dist = 0;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { const int t = C[k][c] - pal[j][c]; dist += t * t; }
+                    if (dist < best) { best = dist; m = (uint32_t)j; }
+                }
+                bits |= eq[k] * m;                                                 // m <= 3: no carry out of a 2-bit field
+            }
+        }
+        out[i] = make_uint2(c0 | (c1 << 16), bits);
+    }
+}
+
 // K3b: mod.rs:114-151 -- RGBA image, pitch 4*nbx pixels; the optional alpha slice overwrites A with the G of its colour
 __global__ void __launch_bounds__(256) etc1s_gather_rgba_kernel(const uint32_t* __restrict__ idx_rgb, const uint32_t* __restrict__ idx_alpha,
                                                                 uint32_t nbx, uint64_t nblocks, const uint32_t* __restrict__ endpoints,
@@ -727,6 +791,15 @@ cudaError_t launch_etc1s_gather_etc1(const uint32_t* idx, uint64_t nblocks, cons
     if (nblocks == 0) return cudaSuccess;
     const uint64_t want = (nblocks + 255) / 256, cap = (uint64_t)sm_count * 16;
     etc1s_gather_etc1_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(idx, nblocks, endpoints, sel_etc1, reinterpret_cast<uint2*>(out));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_etc1s_gather_bc1(const uint32_t* idx, uint64_t nblocks, const uint32_t* endpoints, const uint32_t* sel_plain, void* out,
+                                    int sm_count, cudaStream_t stream)
+{
+    if (nblocks == 0) return cudaSuccess;
+    const uint64_t want = (nblocks + 255) / 256, cap = (uint64_t)sm_count * 16;
+    etc1s_gather_bc1_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(idx, nblocks, endpoints, sel_plain, reinterpret_cast<uint2*>(out));
     return cudaGetLastError();
 }
 

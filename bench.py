@@ -324,7 +324,7 @@ def bench_c4_etc1s(L, b, nb=1024, slices=64, n_cb=4096, reps=2):
            "compressed_bytes_per_slice": len(one), "bits_per_block": 8.0 * len(one) / (nb * nb)}
     buf = ctypes.create_string_buffer(data, len(data))
     import torch
-    for tname, t, ob in (("etc1", 3, 8), ("rgba", 0, 64)):
+    for tname, t, ob in (("etc1", 3, 8), ("bc1", 6, 8), ("rgba", 0, 64)):
         if t == 0 and nblk * 64 > (8 << 30):
             continue
         out = torch.empty(nblk * ob, dtype=torch.uint8).pin_memory()
@@ -345,6 +345,8 @@ def bench_c4_etc1s(L, b, nb=1024, slices=64, n_cb=4096, reps=2):
                                   len(enc["tables"]), 0, ctypes.byref(h)) == 0
         if t == 3:
             e, want = ec.oracle_etc1(orc, h, nb, nb, one)
+        elif t == 6:
+            e, want = ec.oracle_bc1(orc, h, nb, nb, one)       # EXTENSION: no BC1 in the reference, the oracle function is the definition
         else:
             e, want = ec.oracle_rgba(orc, h, nb, nb, one)
         orc.orc_etc1s_close(h)

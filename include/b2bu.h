@@ -38,7 +38,8 @@ enum b2bu_target {
     B2BU_BC7 = 2,  /* BC7        (target_formats/bc7.rs:9)                                16 B/block */
     B2BU_ETC1 = 3, /* ETC1       (target_formats/etc.rs:11)                                8 B/block */
     B2BU_ETC2 = 4, /* ETC2 RGBA  (target_formats/etc.rs:19) = EAC alpha + ETC1 colour     16 B/block */
-    B2BU_UASTC = 5 /* file level only: copy the UASTC payload (basis.rs:175, uastc.rs:85)  16 B/block */
+    B2BU_UASTC = 5,/* file level only: copy the UASTC payload (basis.rs:175, uastc.rs:85)  16 B/block */
+    B2BU_BC1 = 6   /* ETC1S slices only, EXTENSION: the reference has no BC1 (see b2bu_etc1s_transcode_to_bc1) 8 B/block */
 };
 
 enum b2bu_status {
@@ -143,6 +144,14 @@ int b2bu_etc1s_decode_to_rgba(b2bu_etc1s* h, uint32_t nbx, uint32_t nby, const u
 int b2bu_etc1s_transcode_slices(b2bu_etc1s* h, int target, uint32_t nbx, uint32_t nby, const uint8_t* data, size_t data_len,
                                 const uint64_t* slice_ofs, const uint64_t* slice_len, uint32_t num_slices,
                                 uint8_t* out, size_t out_bytes);
+
+/* EXTENSION -- not in the reference.  BASELINE.json names ETC1S -> BC1, but basisu_rs has no BC1 code (only the unused
+ * bc1h0 / bc1h1 hint bits, uastc.rs:31-32), so there is no reference output to be exact to: the result is DEFINED by
+ * oracle/basisu_oracle_etc1s.inc etc1s_emit_bc1 (endpoints = RGB565 of the lowest / highest ETC1S colour the block
+ * uses, selectors remapped to the nearest of the four BC1 palette entries) and the kernel reproduces that bit for bit.
+ * Also reachable as target B2BU_BC1 of b2bu_etc1s_transcode_slices. */
+int b2bu_etc1s_transcode_to_bc1(b2bu_etc1s* h, uint32_t num_blocks_x, uint32_t num_blocks_y, const uint8_t* slice,
+                                size_t slice_len, uint8_t* out, size_t out_bytes);
 
 /* Device-side duration of the phases of the last call on this handle (CUDA events on the call's stream):
  * K2 entropy decode (all slices), K3 codebook gather, and the D2H copy of the result.  The phases are

@@ -16,6 +16,7 @@ def bind(orc):
     orc.orc_etc1s_decode_indices.argtypes = [c.c_void_p, c.c_uint, c.c_uint, c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p]
     orc.orc_etc1s_codebooks.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]
     orc.orc_etc1s_transcode_to_etc1.argtypes = [c.c_void_p, c.c_uint, c.c_uint, c.c_void_p, c.c_size_t, c.c_void_p]
+    orc.orc_etc1s_transcode_to_bc1.argtypes = [c.c_void_p, c.c_uint, c.c_uint, c.c_void_p, c.c_size_t, c.c_void_p]
     orc.orc_etc1s_decode_to_rgba.argtypes = [c.c_void_p, c.c_uint, c.c_uint, c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.c_void_p]
     orc.orc_read_to.argtypes = [c.c_int, c.c_void_p, c.c_size_t, c.c_void_p, c.c_uint32, c.POINTER(c.c_uint32), c.c_void_p, c.c_uint64,
                                 c.POINTER(c.c_uint64), c.c_int]
@@ -41,6 +42,31 @@ def oracle_etc1(orc, h, nbx, nby, data):
     out = np.zeros(nbx * nby * 8, dtype=np.uint8)
     e = orc.orc_etc1s_transcode_to_etc1(h, nbx, nby, data, len(data), out.ctypes.data)
     return e, out.tobytes()
+
+
+def oracle_bc1(orc, h, nbx, nby, data):
+    out = np.zeros(nbx * nby * 8, dtype=np.uint8)
+    e = orc.orc_etc1s_transcode_to_bc1(h, nbx, nby, data, len(data), out.ctypes.data)
+    return e, out.tobytes()
+
+
+def decode_bc1(blocks: bytes, nbx, nby):
+    """Plain BC1 decoder (four-colour and three-colour modes) -> (4 nby, 4 nbx, 3) uint8 image; test helper."""
+    b = np.frombuffer(blocks, dtype=np.uint8).reshape(nby, nbx, 8).astype(np.int32)
+    c = [b[..., 0] | (b[..., 1] << 8), b[..., 2] | (b[..., 3] << 8)]
+    pal = np.zeros((nby, nbx, 4, 3), dtype=np.int32)
+    for e in range(2):
+        r5, g6, b5 = c[e] >> 11, (c[e] >> 5) & 63, c[e] & 31
+        pal[..., e, 0] = (r5 << 3) | (r5 >> 2); pal[..., e, 1] = (g6 << 2) | (g6 >> 4); pal[..., e, 2] = (b5 << 3) | (b5 >> 2)
+    four = (c[0] > c[1])[..., None]
+    pal[..., 2, :] = np.where(four, (2 * pal[..., 0, :] + pal[..., 1, :]) // 3, (pal[..., 0, :] + pal[..., 1, :]) // 2)
+    pal[..., 3, :] = np.where(four, (pal[..., 0, :] + 2 * pal[..., 1, :]) // 3, 0)
+    img = np.zeros((nby * 4, nbx * 4, 3), dtype=np.uint8)
+    for y in range(4):
+        for x in range(4):
+            sel = (b[..., 4 + y] >> (2 * x)) & 3
+            img[y::4, x::4] = np.take_along_axis(pal, sel[..., None, None].repeat(3, -1), axis=2)[..., 0, :]
+    return img
 
 
 def oracle_rgba(orc, h, nbx, nby, rgb, alpha=None):

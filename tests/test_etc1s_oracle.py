@@ -4,7 +4,7 @@ decoder (a restatement of src/basis_lz/mod.rs) must round-trip every construct o
 import numpy as np
 import pytest
 
-from etc1s_common import bind, etc1s_file, make_case, oracle_etc1, oracle_open, oracle_read_to, oracle_rgba, slice_bytes
+from etc1s_common import bind, decode_bc1, etc1s_file, make_case, oracle_bc1, oracle_etc1, oracle_open, oracle_read_to, oracle_rgba, slice_bytes
 
 CASES = [  # nbx, nby, slices, codebook size, history, raw selectors, video
     (16, 16, 2, 64, 64, False, False), (33, 17, 3, 300, 64, True, False), (1, 1, 1, 4, 0, False, False),
@@ -68,3 +68,46 @@ def test_file_level_etc1s_with_alpha_pairs(oracle):
     e, imgs1 = oracle_read_to(orc, 3, f)                    # read_to_etc1 returns every slice, alpha slices included (basis.rs:109-123)
     assert e == 0 and len(imgs1) == 4 and imgs1[0][2] == 8 * nbx
     assert oracle_read_to(orc, 2, f)[0] == 11              # ETC1S -> BC7: reference unimplemented!()
+
+
+def test_bc1_extension_definition_on_a_hand_checkable_block(oracle):
+    """ETC1S -> BC1 is an EXTENSION (absent from the reference); this pins its definition: endpoints = RGB565 of the lowest
+    and highest ETC1S colour in use, selectors remapped to the nearest BC1 palette entry, solid blocks use c0 == c1."""
+    orc = bind(oracle)
+    ep_cb = np.array([[3, 10, 20, 30], [0, 16, 16, 16]], dtype=np.uint8)           # (inten, r5, g5, b5)
+    sel_cb = np.array([[0b11100100, 0b11100100, 0b00011011, 0b11111111], [0b01010101] * 4], dtype=np.uint8)
+    ei = np.array([[0, 1]], dtype=np.uint16)
+    si = np.array([[0, 1]], dtype=np.uint16)
+    from etc1s_synth import encode
+    enc = encode(orc, ep_cb, sel_cb, ei, si, 2, 1, 64)
+    e, h = oracle_open(orc, enc, 2, 2)
+    assert e == 0
+    e, bc1 = oracle_bc1(orc, h, 2, 1, slice_bytes(enc, 0))
+    assert e == 0
+    b0, b1 = bc1[:8], bc1[8:]
+    base = [(10 << 3) | (10 >> 2), (20 << 3) | (20 >> 2), (30 << 3) | (30 >> 2)]
+    lo = [min(255, max(0, v - 42)) for v in base]
+    hi = [min(255, max(0, v + 42)) for v in base]
+    q = lambda c: ((c[0] * 31 + 127) // 255) << 11 | ((c[1] * 63 + 127) // 255) << 5 | ((c[2] * 31 + 127) // 255)
+    c0, c1 = max(q(lo), q(hi)), min(q(lo), q(hi))
+    assert b0[0] | b0[1] << 8 == c0 and b0[2] | b0[3] << 8 == c1 and c0 > c1
+    # selector 3 (brightest) -> palette 0 (c0 = the brighter endpoint here), selector 0 -> palette 1, 2 -> 2, 1 -> 3
+    assert b0[4] == 0b00101101 and b0[5] == 0b00101101 and b0[6] == 0b01111000 and b0[7] == 0
+    # block 1 uses one selector only: solid, c0 == c1, all indices 0
+    assert b1[0:2] == b1[2:4] and b1[4:] == bytes(4)
+    orc.orc_etc1s_close(h)
+
+
+def test_bc1_extension_stays_close_to_the_etc1s_image(oracle):
+    orc = bind(oracle)
+    nbx, nby, ncb = 40, 24, 512
+    _, _, ei, si, enc = make_case(orc, nbx, nby, 1, ncb, seed=9)
+    e, h = oracle_open(orc, enc, ncb, ncb)
+    d = slice_bytes(enc, 0)
+    e, bc1 = oracle_bc1(orc, h, nbx, nby, d)
+    assert e == 0
+    _, rgba = oracle_rgba(orc, h, nbx, nby, d)
+    ref = np.frombuffer(rgba, dtype=np.uint8).reshape(nby * 4, nbx * 4, 4)[..., :3].astype(np.int32)
+    err = np.abs(decode_bc1(bc1, nbx, nby).astype(np.int32) - ref)
+    assert err.mean() < 9.0 and err.max() <= 96      # random codebooks: many high-intensity tables whose clamped colours leave the BC1 line
+    orc.orc_etc1s_close(h)

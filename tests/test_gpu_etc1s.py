@@ -5,7 +5,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from etc1s_common import bind, etc1s_file, make_case, oracle_etc1, oracle_open, oracle_read_to, oracle_rgba, slice_bytes
+from etc1s_common import bind, decode_bc1, etc1s_file, make_case, oracle_bc1, oracle_etc1, oracle_open, oracle_read_to, oracle_rgba, slice_bytes
 
 pytestmark = pytest.mark.gpu
 
@@ -99,6 +99,24 @@ def test_file_level_large_file_device_crc_path(gpu_lib, oracle):
     with pytest.raises(gpu_lib.BasisuError) as ei_:
         gpu_lib.read_to_rgba(bytes(g))
     assert str(ei_.value) == "Data CRC16 failed"
+
+
+@pytest.mark.parametrize("nbx,nby,ncb", [(64, 64, 4096), (33, 17, 300), (1, 1, 4)])
+def test_bc1_extension_matches_its_definition(gpu_lib, oracle, nbx, nby, ncb):
+    """ETC1S -> BC1 does not exist in the reference: the definition is the oracle's etc1s_emit_bc1; the kernel must
+    reproduce it bit for bit (the sanity of the definition itself is a CPU test, tests/test_etc1s_oracle.py)."""
+    orc = bind(oracle)
+    _, _, ei, si, enc = make_case(orc, nbx, nby, 2, ncb, seed=nbx * 7 + nby)
+    e, h = oracle_open(orc, enc, ncb, ncb)
+    dec = gpu_lib.Etc1sDecoder(ncb, ncb, enc["endpoints"], enc["selectors"], enc["tables"])
+    for k in range(2):
+        d = slice_bytes(enc, k)
+        e, want = oracle_bc1(orc, h, nbx, nby, d)
+        assert e == 0
+        got = dec.transcode_to_bc1(nbx, nby, d)
+        assert got == want
+    dec.close()
+    orc.orc_etc1s_close(h)
 
 
 def test_corrupt_streams_report_like_the_oracle(gpu_lib, oracle):
