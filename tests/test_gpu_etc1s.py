@@ -145,6 +145,45 @@ def test_corrupt_streams_report_like_the_oracle(gpu_lib, oracle):
     orc.orc_etc1s_close(h)
 
 
+@pytest.mark.parametrize("nbx,nby,ncb,hist,video", [(64, 20, 300, 64, False), (37, 9, 40, 16, False), (32, 6, 64, 64, True), (95, 4, 2000, 0, False)])
+def test_corrupt_stream_fuzz_keeps_the_reference_error_order(gpu_lib, oracle, nbx, nby, ncb, hist, video):
+    """The two-warp pipeline finds errors in two places (bit-level in the tokenizer, index-level in the resolver) and must
+    still report the one the reference's serial loop meets first; and streams that decode despite the damage must decode
+    to the same indices.  Bit flips, byte splices and truncations over several shapes (odd widths, video, no history)."""
+    orc = bind(oracle)
+    _, _, ei, si, enc = make_case(orc, nbx, nby, 1, ncb, hist, False, video, seed=nbx + 3 * nby)
+    e, h = oracle_open(orc, enc, ncb, ncb, video)
+    assert e == 0
+    dec = gpu_lib.Etc1sDecoder(ncb, ncb, enc["endpoints"], enc["selectors"], enc["tables"], b"", video)
+    good = slice_bytes(enc, 0)
+    rng = np.random.default_rng(nbx * 1000 + nby)
+    seen = set()
+    for trial in range(40):
+        bad = bytearray(good)
+        kind = trial % 4
+        if kind == 0:
+            bad = bad[: int(rng.integers(0, len(bad)))]
+        elif kind == 1:
+            bad[int(rng.integers(0, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 2:
+            at = int(rng.integers(0, len(bad)))
+            bad[at:at + 4] = bytes(rng.integers(0, 256, size=4, dtype=np.uint8))
+        else:
+            at = int(rng.integers(0, max(1, len(bad) - 8)))
+            bad[at:at + 8] = b"\xff" * 8
+        e, want = oracle_etc1(orc, h, nbx, nby, bytes(bad))
+        seen.add(e)
+        if e == 0:
+            assert dec.transcode_to_etc1(nbx, nby, bytes(bad)) == want, trial
+        else:
+            with pytest.raises(gpu_lib.BasisuError) as ei_:
+                dec.transcode_to_etc1(nbx, nby, bytes(bad))
+            assert ei_.value.status == e, (trial, kind)
+    assert len(seen) >= 2
+    dec.close()
+    orc.orc_etc1s_close(h)
+
+
 def test_config4_shape_slices_property(gpu_lib, oracle):
     """BASELINE config 4 shape (1024x1024 blocks per slice) on a few slices: decode -> re-encode round trip
     is not available, so check against the oracle on one slice and self-consistency (ETC1 vs RGBA colours)."""
