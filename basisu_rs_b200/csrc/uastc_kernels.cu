@@ -115,6 +115,9 @@ __constant__ uint8_t kBinOrder[32] = {3, 9, 16, 4, 7, 2, 12, 10, 11, 13, 14, 6, 
 #ifndef B2BU_TILE_RGBA
 #define B2BU_TILE_RGBA 1024
 #endif
+#ifndef B2BU_TILE_ETC1
+#define B2BU_TILE_ETC1 B2BU_TILE16
+#endif
 #ifndef B2BU_SORT_WARPS
 #define B2BU_SORT_WARPS 8
 #endif
@@ -142,11 +145,16 @@ __device__ unsigned long long g_trace[160][64];
 #define B2BU_DMA_WAIT(bar, parity) mbar_wait((bar), (parity))
 #endif
 
+#ifndef B2BU_SLOTS
+#define B2BU_SLOTS 2
+#endif
+
 template <int TARGET> struct PipeCfg {
+    static constexpr int NS = B2BU_SLOTS;                                   // tile slots in flight (load / sort / work / store)
     static constexpr int OB = TARGET == TGT_RGBA ? 64 : TARGET == TGT_ETC1 ? 8 : 16;
     static constexpr bool IN_PLACE = OB == 16;
     static constexpr bool DYNAMIC = TARGET != TGT_ASTC;
-    static constexpr int TILE = TARGET == TGT_RGBA ? B2BU_TILE_RGBA : B2BU_TILE16;
+    static constexpr int TILE = TARGET == TGT_RGBA ? B2BU_TILE_RGBA : TARGET == TGT_ETC1 ? B2BU_TILE_ETC1 : B2BU_TILE16;
     static constexpr int SORT_WARPS = B2BU_SORT_WARPS;
     static constexpr int SORT_THREADS = SORT_WARPS * 32;
     static constexpr int WORK_WARPS = B2BU_WORK_WARPS;
@@ -155,15 +163,15 @@ template <int TARGET> struct PipeCfg {
     static constexpr int MAXORD = TILE + kBins * 32;
     static constexpr int MAXITEMS = MAXORD / 32;
     static constexpr size_t OFF_IN = (TableBytes<TARGET>::value + 127) / 128 * 128;   // two slots
-    static constexpr size_t OFF_OUT = OFF_IN + 2 * (size_t)TILE * 16;                  // staging for ETC1 / RGBA, two slots
+    static constexpr size_t OFF_OUT = OFF_IN + NS * (size_t)TILE * 16;                 // staging for ETC1 / RGBA, one per slot
     static constexpr size_t OUT_SLOT = IN_PLACE ? 0 : (size_t)TILE * OB;
-    static constexpr size_t OFF_ORDER = OFF_OUT + 2 * OUT_SLOT;
-    static constexpr size_t OFF_INFO = OFF_ORDER + 2 * (size_t)MAXORD * 2;
-    static constexpr size_t OFF_WCNT = (OFF_INFO + 2 * 32 * 4 + 15) / 16 * 16;
+    static constexpr size_t OFF_ORDER = OFF_OUT + NS * OUT_SLOT;
+    static constexpr size_t OFF_INFO = OFF_ORDER + NS * (size_t)MAXORD * 2;
+    static constexpr size_t OFF_WCNT = (OFF_INFO + NS * 32 * 4 + 15) / 16 * 16;
     static constexpr size_t OFF_BASE = OFF_WCNT + (size_t)SORT_WARPS * 32 * 4;
     static constexpr size_t OFF_CTL = OFF_BASE + (size_t)SORT_WARPS * 32 * 4;
-    static constexpr size_t OFF_BAR = OFF_CTL + 2 * 4 * 4;
-    static constexpr size_t SMEM = OFF_BAR + 6 * 8;
+    static constexpr size_t OFF_BAR = (OFF_CTL + NS * 4 * 4 + 7) / 8 * 8;
+    static constexpr size_t SMEM = OFF_BAR + 3 * NS * 8;
     static_assert(SMEM <= 227 * 1024, "tile configuration does not fit shared memory");
     static_assert(THREADS <= 1024, "too many warps");
 };
@@ -192,7 +200,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
     uint32_t* wbase = reinterpret_cast<uint32_t*>(smem + C::OFF_BASE);        // [SORT_WARPS][32]
     uint32_t* ctl = reinterpret_cast<uint32_t*>(smem + C::OFF_CTL);           // [2][4]: next item, number of items
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);          // full[2], sorted[2], done[2]
-    uint64_t* bar_full = bars, *bar_sorted = bars + 2, *bar_done = bars + 4;
+    uint64_t* bar_full = bars, *bar_sorted = bars + C::NS, *bar_done = bars + 2 * C::NS;
 
     // role order by hardware warp id: B2BU_SORT_FIRST = 1 puts the sorter warps at the low ids
 #ifndef B2BU_SORT_FIRST
@@ -223,9 +231,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
     auto tile_blocks = [&](uint32_t k) -> uint32_t { return tile_start(k + 1) - tile_start(k); };
 
     if (tid == 0) {
-        mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
-        mbar_init(&bar_sorted[0], 1); mbar_init(&bar_sorted[1], 1);
-        mbar_init(&bar_done[0], C::WORK_WARPS); mbar_init(&bar_done[1], C::WORK_WARPS);
+        for (int i = 0; i < C::NS; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_sorted[i], 1); mbar_init(&bar_done[i], C::WORK_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     load_tables(&T, TableBytes<TARGET>::value);  // ends with __syncthreads()
@@ -235,7 +241,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
         // ================================ DMA warp ================================
         if (lane != 0) return;
         auto store_tile = [&](uint32_t k) {
-            const uint32_t s = k & 1u, nt = tile_blocks(k);
+            const uint32_t s = k % C::NS, nt = tile_blocks(k);
             const uint64_t g0 = r0 + tile_start(k);
             fence_async_smem();
             if (TARGET == TGT_RGBA) {
@@ -262,10 +268,10 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
             tma_store_commit();
         };
         for (uint32_t k = 0; k < ntiles; k++) {
-            const uint32_t s = k & 1u, u = k >> 1;
-            if (k >= 2) {                                      // slot reuse: tile k-2 must be finished and stored
+            const uint32_t s = k % C::NS, u = k / C::NS;
+            if (k >= (uint32_t)C::NS) {                        // slot reuse: tile k-NS must be finished and stored
                 B2BU_DMA_WAIT(&bar_done[s], (u - 1u) & 1u);
-                store_tile(k - 2);
+                store_tile(k - C::NS);
                 tma_store_wait_read();
             }
             const uint32_t bytes = tile_blocks(k) * 16u;
@@ -273,8 +279,8 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
             tma_load_1d(in_s + s * C::TILE, in + r0 + tile_start(k), bytes, &bar_full[s]);
             do { if (k < 6) TRACE(k * 6 + 0); } while (0);
         }
-        for (uint32_t k = ntiles >= 2 ? ntiles - 2 : 0; k < ntiles; k++) {
-            B2BU_DMA_WAIT(&bar_done[k & 1u], (k >> 1) & 1u);
+        for (uint32_t k = ntiles >= (uint32_t)C::NS ? ntiles - C::NS : 0; k < ntiles; k++) {
+            B2BU_DMA_WAIT(&bar_done[k % C::NS], (k / C::NS) & 1u);
             store_tile(k);
         }
         tma_store_wait_all();
@@ -287,7 +293,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
         const int sw = warp - C::WORK_WARPS, st = sw * 32 + lane;
         uint32_t* mycnt = wcnt + sw * 32;
         for (uint32_t k = 0; k < ntiles; k++) {
-            const uint32_t s = k & 1u, u = k >> 1, nt = tile_blocks(k);
+            const uint32_t s = k % C::NS, u = k / C::NS, nt = tile_blocks(k);
             const uint4* tin = in_s + s * C::TILE;
             mycnt[lane] = 0;
             __syncwarp();
@@ -374,7 +380,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
 
     // ================================ worker warps ================================
     for (uint32_t k = 0; k < ntiles; k++) {
-        const uint32_t s = k & 1u, u = k >> 1;
+        const uint32_t s = k % C::NS, u = k / C::NS;
         uint4* tin = in_s + s * C::TILE;
         unsigned char* tout = out_s + s * C::OUT_SLOT;
         const uint16_t* ord = order + s * C::MAXORD;
