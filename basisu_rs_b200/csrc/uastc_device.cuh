@@ -1095,35 +1095,35 @@ B2BU_DI uint2 etc2_alpha_block(const uint32_t (&px)[16], uint32_t etc2tm, const 
     return r;
 }
 
-// etc.rs:203-259 apply_etc1_bias for one channel
-B2BU_DI int etc1_bias_delta(uint32_t bias, int c, uint32_t subblock)
+// etc.rs:203-259 apply_etc1_bias for one channel.  The reference's 32-way match on the bias index is a table here
+// (a switch diverges up to 32 ways inside a warp): per bias, 2 bits (delta + 2) for each (sub-block, channel).
+constexpr int etc1_bias_delta_ref(uint32_t bias, int c, bool s1)
 {
-    const bool s1 = subblock == 1u;
-    switch (bias) {
-    case 2:  return s1 ? 0 : (c == 0 ? -1 : 0);
-    case 5:  return s1 ? 0 : (c == 1 ? -1 : 0);
-    case 6:  return s1 ? 0 : (c == 2 ? -1 : 0);
-    case 7:  return s1 ? 0 : (c == 0 ? 1 : 0);
-    case 11: return s1 ? 0 : (c == 1 ? 1 : 0);
-    case 15: return s1 ? 0 : (c == 2 ? 1 : 0);
-    case 18: return s1 ? (c == 0 ? -1 : 0) : 0;
-    case 19: return s1 ? (c == 1 ? -1 : 0) : 0;
-    case 20: return s1 ? (c == 2 ? -1 : 0) : 0;
-    case 21: return s1 ? (c == 0 ? 1 : 0) : 0;
-    case 24: return s1 ? (c == 1 ? 1 : 0) : 0;
-    case 8:  return s1 ? (c == 2 ? 1 : 0) : 0;
-    case 10: return -2;
-    case 27: return s1 ? 0 : -1;
-    case 28: return s1 ? -1 : 1;
-    case 29: return s1 ? 1 : 0;
-    case 30: return s1 ? -1 : 0;
-    case 31: return s1 ? 0 : 1;
-    default: return (int)((bias / (c == 0 ? 1u : c == 1 ? 3u : 9u)) % 3u) - 1;
-    }
+    return bias == 2 ? (s1 ? 0 : (c == 0 ? -1 : 0)) : bias == 5 ? (s1 ? 0 : (c == 1 ? -1 : 0)) : bias == 6 ? (s1 ? 0 : (c == 2 ? -1 : 0))
+         : bias == 7 ? (s1 ? 0 : (c == 0 ? 1 : 0)) : bias == 11 ? (s1 ? 0 : (c == 1 ? 1 : 0)) : bias == 15 ? (s1 ? 0 : (c == 2 ? 1 : 0))
+         : bias == 18 ? (s1 ? (c == 0 ? -1 : 0) : 0) : bias == 19 ? (s1 ? (c == 1 ? -1 : 0) : 0) : bias == 20 ? (s1 ? (c == 2 ? -1 : 0) : 0)
+         : bias == 21 ? (s1 ? (c == 0 ? 1 : 0) : 0) : bias == 24 ? (s1 ? (c == 1 ? 1 : 0) : 0) : bias == 8 ? (s1 ? (c == 2 ? 1 : 0) : 0)
+         : bias == 10 ? -2 : bias == 27 ? (s1 ? 0 : -1) : bias == 28 ? (s1 ? -1 : 1) : bias == 29 ? (s1 ? 1 : 0) : bias == 30 ? (s1 ? -1 : 0)
+         : bias == 31 ? (s1 ? 0 : 1) : (int)((bias / (c == 0 ? 1u : c == 1 ? 3u : 9u)) % 3u) - 1;
 }
-B2BU_DI uint32_t etc1_apply_bias(uint32_t v0, uint32_t bias, int c, uint32_t limit, uint32_t subblock)
+constexpr uint32_t etc1_bias_word(uint32_t bias)
 {
-    const int delta = etc1_bias_delta(bias, c, subblock);
+    uint32_t w = 0;
+    for (int sb = 0; sb < 2; sb++)
+        for (int c = 0; c < 3; c++) w |= (uint32_t)(etc1_bias_delta_ref(bias, c, sb == 1) + 2) << (2 * (sb * 3 + c));
+    return w;
+}
+#define B2BU_BW(i) (uint16_t)etc1_bias_word(i)
+static __device__ const uint16_t kEtc1BiasLut[32] = {
+    B2BU_BW(0), B2BU_BW(1), B2BU_BW(2), B2BU_BW(3), B2BU_BW(4), B2BU_BW(5), B2BU_BW(6), B2BU_BW(7), B2BU_BW(8), B2BU_BW(9), B2BU_BW(10),
+    B2BU_BW(11), B2BU_BW(12), B2BU_BW(13), B2BU_BW(14), B2BU_BW(15), B2BU_BW(16), B2BU_BW(17), B2BU_BW(18), B2BU_BW(19), B2BU_BW(20),
+    B2BU_BW(21), B2BU_BW(22), B2BU_BW(23), B2BU_BW(24), B2BU_BW(25), B2BU_BW(26), B2BU_BW(27), B2BU_BW(28), B2BU_BW(29), B2BU_BW(30),
+    B2BU_BW(31)};
+#undef B2BU_BW
+// bw: the block's kEtc1BiasLut entry
+B2BU_DI uint32_t etc1_apply_bias(uint32_t v0, uint32_t bw, int c, uint32_t limit, uint32_t subblock)
+{
+    const int delta = (int)((bw >> (2 * ((int)subblock * 3 + c))) & 3u) - 2;
     int v = (int)v0;
     if (v == 0) v += (delta == -2) ? 3 : delta + 1;
     else if (v == (int)limit) v += delta - 1;
@@ -1153,8 +1153,9 @@ B2BU_DI uint2 etc1_block(const uint32_t (&px)[16], const EtcFlags& f, const DevT
     c0[0] = ((rb0 & 0xFFFFu) * limit + 1020u) / 2040u; c0[1] = (g0 * limit + 1020u) / 2040u; c0[2] = ((rb0 >> 16) * limit + 1020u) / 2040u;
     c1[0] = ((rb1 & 0xFFFFu) * limit + 1020u) / 2040u; c1[1] = (g1 * limit + 1020u) / 2040u; c1[2] = ((rb1 >> 16) * limit + 1020u) / 2040u;
     if (f.has_bias) {
+        const uint32_t bw = kEtc1BiasLut[f.bias & 31u];
 #pragma unroll
-        for (int c = 0; c < 3; c++) { c0[c] = etc1_apply_bias(c0[c], f.bias, c, limit, 0u); c1[c] = etc1_apply_bias(c1[c], f.bias, c, limit, 1u); }
+        for (int c = 0; c < 3; c++) { c0[c] = etc1_apply_bias(c0[c], bw, c, limit, 0u); c1[c] = etc1_apply_bias(c1[c], bw, c, limit, 1u); }
     }
     uint32_t base0[3], base1[3], hdr = 0;
     if (!f.diff) {
@@ -1200,6 +1201,8 @@ B2BU_DI uint2 etc1_block(const uint32_t (&px)[16], const EtcFlags& f, const DevT
 #pragma unroll
     for (int k = 0; k < 3; k++) { thr_tr[k] = flip ? thr[0][k] : thr[1][k]; thr_bl[k] = flip ? thr[1][k] : thr[0][k]; }
 
+    // selector s = #(lum >= t_k); its ETC1 code [3,2,0,1] (etc.rs:433) has msb = (s < 2) = (lum < t1) and
+    // lsb = (s == 0 || s == 3) = (lum < t0) || (lum >= t2): three compares and two conditional ORs per texel
     uint32_t selbits = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
@@ -1208,13 +1211,12 @@ B2BU_DI uint2 etc1_block(const uint32_t (&px)[16], const EtcFlags& f, const DevT
         const int t0 = (qx == qy) ? thr[qx][0] : (qx ? thr_tr[0] : thr_bl[0]);
         const int t1 = (qx == qy) ? thr[qx][1] : (qx ? thr_tr[1] : thr_bl[1]);
         const int t2 = (qx == qy) ? thr[qx][2] : (qx ? thr_tr[2] : thr_bl[2]);
-        const int lum = (int)(px[i] & 0xFFu) * 108 + (int)((px[i] >> 8) & 0xFFu) * 366 + (int)((px[i] >> 16) & 0xFFu) * 38;
-        const uint32_t sel = (uint32_t)(lum >= t0) + (uint32_t)(lum >= t1) + (uint32_t)(lum >= t2);
-        // selector -> ETC1 code [3,2,0,1]: msb = sel < 2, lsb = (sel == 0 || sel == 3)   (etc.rs:433)
-        const uint32_t msb = sel < 2u ? 1u : 0u, lsb = (sel == 0u || sel == 3u) ? 1u : 0u;
+        // 108 R + 366 G + 38 B as two byte dot products (366 = 2 x 183 does not fit a signed byte weight)
+        const int lum = __dp4a(px[i], 0x0026B76Cu, __dp4a(px[i], 0x0000B700u, 0u));
         const int pid = x * 4 + y;
         const int bitpos = pid < 8 ? 8 + pid : pid - 8;  // byte 1 holds pixels 0..7, byte 0 pixels 8..15
-        selbits |= (msb << bitpos) | (lsb << (16 + bitpos));
+        if (lum < t1) selbits |= 1u << bitpos;
+        if (lum < t0 || lum >= t2) selbits |= 1u << (16 + bitpos);
     }
     return make_uint2(hdr, selbits);
 }

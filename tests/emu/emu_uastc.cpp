@@ -34,6 +34,12 @@ static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel)
     for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
     return r;
 }
+// unsigned bytes of a times unsigned bytes of b (the kernel only uses weights < 256 as u8 x u8), accumulated
+static inline uint32_t __dp4a(uint32_t a, uint32_t b, uint32_t c)
+{
+    for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xFF) * ((b >> (8 * i)) & 0xFF);
+    return c;
+}
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
