@@ -387,7 +387,7 @@ template <int M> B2BU_DI void canon_front(const uint4& b, const DevTables& T, ui
 B2BU_DI uint32_t lerp2_raw(uint32_t lo, uint32_t hi, uint32_t w, uint32_t iw)
 {
     const uint32_t t = lo * iw + hi * w;
-    return t + (((t + 0x00200020u) >> 8) & 0x00FF00FFu);
+    return t + __byte_perm(t + 0x00200020u, 0u, 0x4341);        // ((t + 32) >> 8) per 16-bit lane: bytes 1 and 3 moved down, one PRMT
 }
 
 // One row of four texels.  MULTI: more than one subset; DUAL: two weight planes.
@@ -1142,7 +1142,7 @@ B2BU_DI uint2 etc1_block(const uint32_t (&px)[16], const EtcFlags& f, const DevT
     for (int i = 0; i < 16; i++) {
         const int x = i & 3, y = i >> 2;
         srb[y >> 1][x >> 1] += px[i] & 0x00FF00FFu;
-        sg[y >> 1][x >> 1] += (px[i] >> 8) & 0xFFu;
+        sg[y >> 1][x >> 1] = __dp4a(px[i], 0x00000100u, sg[y >> 1][x >> 1]);       // += G
     }
     const bool flip = f.flip != 0u;
     // sub-block 0 = TL + (flip ? TR : BL), sub-block 1 = BR + (flip ? BL : TR)
