@@ -1076,15 +1076,31 @@ B2BU_DI uint2 etc2_alpha_block(const uint32_t (&px)[16], uint32_t etc2tm, const 
     int vals[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) { const int v = center + (int)T.eac_mod[ti][k] * mult; vals[k] = v < 0 ? 0 : v > 255 ? 255 : v; }
+    // Nearest of the 8 values, lowest index on ties (etc.rs:317-323 min_by_key).  In value order the candidates are
+    // k = 3,2,1,0,4,5,6,7 (the table rows are {-m0..-m3, m0-1..m3-1} with m increasing, clamping keeps the order), so the
+    // answer is the number of boundaries between neighbours that the texel's alpha passes: below k = 0 a tie goes to the
+    // higher value (= lower index), from k = 0 upwards to the lower one.  7 compares per texel instead of
+    // 8 x (difference, abs, key, min); tests/test_emu_kernels.py checks the rule exhaustively.
+    const int sv[8] = {vals[3], vals[2], vals[1], vals[0], vals[4], vals[5], vals[6], vals[7]};
+    int thr[7];
+#pragma unroll
+    for (int j = 6; j >= 0; j--) {
+        const int sum = sv[j] + sv[j + 1];
+        const bool same = sv[j] == sv[j + 1];
+        // equal neighbours: below k = 0 the boundary is always passed (towards the lower index); above, it is passed together
+        // with the next one (a texel only moves past a duplicate when a later, different value is strictly closer)
+        thr[j] = j < 3 ? (same ? 0 : (sum + 1) >> 1) : (same ? (j == 6 ? 256 : thr[j < 6 ? j + 1 : 6]) : (sum >> 1) + 1);
+    }
     uint64_t sel = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const int a = (int)(px[i] >> 24);
-        uint32_t best = 0xFFFFFFFFu;                     // (|diff| << 3) | index: min() keeps the first minimum
+        uint32_t p = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) best = min(best, ((uint32_t)abs(vals[k] - a) << 3) | (uint32_t)k);
+        for (int j = 0; j < 7; j++) p += a >= thr[j] ? 1u : 0u;
+        const uint32_t best = (0x76540123u >> (4u * p)) & 7u;
         const int x = i / 4, y = i % 4, id = y * 4 + x;  // etc.rs:325-329 (transposed pixel order)
-        sel |= (uint64_t)(best & 7u) << (45 - id * 3);
+        sel |= (uint64_t)best << (45 - id * 3);
     }
     // bytes: centre, etc2tm, then selectors big-endian (48 bits)
     const uint32_t s47_40 = (uint32_t)(sel >> 40) & 0xFFu, s39_32 = (uint32_t)(sel >> 32) & 0xFFu;
