@@ -13,6 +13,7 @@ CASES = [  # nbx, nby, slices, codebook size, history, raw selectors, video
     (16, 16, 2, 64, 64, False, False), (33, 17, 3, 300, 64, True, False), (1, 1, 1, 4, 0, False, False), (2, 1, 1, 4, 64, False, False),
     (64, 64, 2, 4096, 64, False, False), (7, 5, 2, 50, 16, False, True), (128, 96, 2, 1000, 200, False, False), (31, 1, 1, 20, 64, False, False),
     (1, 40, 1, 20, 64, False, False), (257, 130, 1, 8000, 64, False, False),
+    (60001, 3, 1, 300, 64, False, False),          # wider than the shared-memory row state: previous-row state in the global scratch area
 ]
 
 
