@@ -5,6 +5,7 @@
 // slice table, the UASTC slices transcoded in place in that upload -- slices that are contiguous in
 // the file (a mip chain) in one launch -- and ONE copy back.  Small files keep the host CRC (a
 // launch and a sync cost more than a few KB of table lookups).
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -59,6 +60,8 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // files at least this long are uploaded whole and CRC-checked by the GPU
 constexpr size_t kGpuCrcMinBytes = 256 * 1024;
+// piece size of the pipelined upload
+constexpr size_t kFilePieceBytes = 8u << 20;
 
 }  // namespace b2bu
 
@@ -104,8 +107,9 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
     // basis.rs:338-341.  Large files: the transcoding call computes the CRC on the device; a pure sizing call (out == NULL)
     // of a large file leaves the data CRC to the transcoding call that follows it.
     const bool big = len >= kGpuCrcMinBytes;
-    const bool gpu_crc = big && out != nullptr;
-    if (!big && crc16_host(buf + 77, len - 77, 0) != h.data_crc16) return B2BU_ERR_DATA_CRC;
+    const bool plain_copy = h.tex_format == 1 && target == B2BU_UASTC;              // read_to_uastc never needs the device
+    const bool gpu_crc = big && out != nullptr && !plain_copy;
+    if ((!big || (out != nullptr && plain_copy)) && crc16_host(buf + 77, len - 77, 0) != h.data_crc16) return B2BU_ERR_DATA_CRC;
 
     DeviceCtx* c = nullptr;
     std::unique_lock<std::mutex> lk;
@@ -120,11 +124,18 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
         if ((uint64_t)h.slice_desc_file_ofs + 23 <= len && h.total_slices) phase = parse_slice_desc(buf + h.slice_desc_file_ofs).file_ofs & 15u;
         d_file = static_cast<uint8_t*>(c->d_file) + ((16u - phase) & 15u);
         s0 = c->streams[0];
-        CK(cudaMemcpyAsync(d_file, buf, len, cudaMemcpyHostToDevice, s0));
         CK(cudaMemsetAsync(c->d_crc, 0, sizeof(uint32_t), s0));
+    }
+    // whole-file upload + CRC in one piece (ETC1S files, and UASTC files whose slices cannot be transcoded in place)
+    bool uploaded = false;
+    auto upload_all = [&]() -> int {
+        if (!gpu_crc || uploaded) return B2BU_OK;
+        uploaded = true;
+        CK(cudaMemcpyAsync(d_file, buf, len, cudaMemcpyHostToDevice, s0));
         CK(launch_crc16_dev(d_file + 77, len - 77, c->d_crc, c->sm_count, s0));
         count_launch(1);
-    }
+        return B2BU_OK;
+    };
     // everything below is the body after the CRC check; with the device CRC in flight its status is held back until the CRC is known
     auto body = [&]() -> int {
     // basis.rs:343-362 read_slice_descs
@@ -183,7 +194,11 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
         for (uint32_t i = 0; i < nimg; i++) memcpy(out + plan[i].offset, buf + descs[i].file_ofs, descs[i].file_size);
         return B2BU_OK;
     }
-    if (etc1s) return etc1s_read_file(target, buf, len, h, descs.data(), plan.data(), nimg, pair, out, d_file);
+    if (etc1s) {
+        int stu = upload_all();
+        if (stu) return stu;
+        return etc1s_read_file(target, buf, len, h, descs.data(), plan.data(), nimg, pair, out, d_file);
+    }
 
     // ---- UASTC file ------------------------------------------------------------------------------
     int st2;
@@ -199,17 +214,73 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
         in_place = descs[i].file_size == 0 || ((reinterpret_cast<uintptr_t>(d_file) + descs[i].file_ofs) & 15) == 0;
     CK(cudaMemsetAsync(c->d_err, 0xFF, sizeof(unsigned long long), s0));
     if (in_place) {
+        // Pipelined: the file goes up in pieces on the copy-in stream; behind every piece the kernel stream adds the piece
+        // to the CRC and transcodes the blocks that are now complete (whole block rows for RGBA), and the copy-out stream
+        // returns them -- upload, kernels and download of different pieces overlap (PCIe is full duplex).
         if ((st2 = ensure(&c->d_out[0], &c->out_cap[0], total))) return st2;
-        std::vector<b2bu_slice_dev> sl(nimg);
+        uploaded = true;
+        cudaStream_t sH = c->streams[0], sK = c->streams[1], sD = c->streams[2];
         const uint8_t* abase = static_cast<const uint8_t*>(c->d_file);              // 256-byte aligned
-        for (uint32_t i = 0; i < nimg; i++)
-            sl[i] = {descs[i].file_size ? (uint64_t)(d_file + descs[i].file_ofs - abase) : 0u, plan[i].offset, descs[i].file_size / 16, descs[i].num_blocks_x, 0u};
-        if ((st2 = b2bu_uastc_transcode_slices_dev(target, abase, c->d_out[0], sl.data(), nimg, c->d_err, s0))) return st2;
-        CK(cudaMemcpyAsync(out, c->d_out[0], total, cudaMemcpyDeviceToHost, s0));
-        CK(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s0));
-        CK(cudaStreamSynchronize(s0));
+        uint8_t* d_out = static_cast<uint8_t*>(c->d_out[0]);
+        const uint64_t ob = b2bu_block_bytes(target);
+        std::vector<uint64_t> done_blocks(nimg, 0), base_blocks(nimg, 0);
+        for (uint32_t i = 1; i < nimg; i++) base_blocks[i] = base_blocks[i - 1] + descs[i - 1].file_size / 16;
+        std::vector<cudaEvent_t> evs;
+        auto new_event = [&](cudaStream_t s) -> cudaEvent_t { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); cudaEventRecord(e, s); evs.push_back(e); return e; };
+        cudaStreamWaitEvent(sK, new_event(s0), 0);                                  // the status / CRC words are reset on s0
+        int rc = B2BU_OK;
+        for (uint64_t pos = 0; pos < len && rc == B2BU_OK;) {
+            const uint64_t n = std::min<uint64_t>(kFilePieceBytes, len - pos);
+            if (cudaMemcpyAsync(d_file + pos, buf + pos, n, cudaMemcpyHostToDevice, sH) != cudaSuccess) { rc = B2BU_ERR_CUDA; break; }
+            cudaStreamWaitEvent(sK, new_event(sH), 0);
+            const uint64_t up = pos + n;                                            // file bytes [0, up) are on the device
+            if (up > 77) {
+                const uint64_t from = std::max<uint64_t>(pos, 77);
+                if (launch_crc16_dev(d_file + from, up - from, c->d_crc, c->sm_count, sK, len - up) != cudaSuccess) { rc = B2BU_ERR_CUDA; break; }
+                count_launch(1);
+            }
+            // blocks that became complete with this piece, slice by slice; contiguous slices merge into one launch
+            std::vector<b2bu_slice_dev> sl;
+            std::vector<uint32_t> which;
+            for (uint32_t i = 0; i < nimg; i++) {
+                const uint64_t nb = descs[i].file_size / 16;
+                if (done_blocks[i] == nb || up <= descs[i].file_ofs) continue;
+                uint64_t avail = std::min<uint64_t>(nb, (up - descs[i].file_ofs) / 16);
+                if (target == B2BU_RGBA) avail = avail / descs[i].num_blocks_x * descs[i].num_blocks_x;
+                if (avail <= done_blocks[i]) continue;
+                sl.push_back({(uint64_t)(d_file + descs[i].file_ofs - abase) + done_blocks[i] * 16, plan[i].offset + done_blocks[i] * ob,
+                              avail - done_blocks[i], descs[i].num_blocks_x, 0u});
+                which.push_back(i);
+            }
+            if (!sl.empty()) {
+                // the status word numbers blocks through the file: one call per run of slices that is contiguous in that numbering
+                size_t a = 0;
+                while (a < sl.size() && rc == B2BU_OK) {
+                    size_t b = a + 1;
+                    while (b < sl.size() && base_blocks[which[b]] + done_blocks[which[b]] == base_blocks[which[b - 1]] + done_blocks[which[b - 1]] + sl[b - 1].nblocks) b++;
+                    rc = uastc_transcode_slices_based(target, abase, d_out, sl.data() + a, (uint32_t)(b - a), base_blocks[which[a]] + done_blocks[which[a]], c->d_err, sK);
+                    a = b;
+                }
+                if (rc != B2BU_OK) break;
+                cudaStreamWaitEvent(sD, new_event(sK), 0);
+                for (size_t k = 0; k < sl.size(); k++) {
+                    if (cudaMemcpyAsync(out + sl[k].out_ofs, d_out + sl[k].out_ofs, sl[k].nblocks * ob, cudaMemcpyDeviceToHost, sD) != cudaSuccess) { rc = B2BU_ERR_CUDA; break; }
+                    done_blocks[which[k]] += sl[k].nblocks;
+                }
+            }
+            pos = up;
+        }
+        // everything funnels back into s0, where the caller waits for the CRC word
+        cudaStreamWaitEvent(s0, new_event(sK), 0);
+        cudaStreamWaitEvent(s0, new_event(sD), 0);
+        if (rc == B2BU_OK && cudaMemcpyAsync(c->h_err, c->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s0) != cudaSuccess) rc = B2BU_ERR_CUDA;
+        const cudaError_t es = cudaStreamSynchronize(s0);
+        for (cudaEvent_t e : evs) cudaEventDestroy(e);
+        if (rc != B2BU_OK) return rc == B2BU_ERR_CUDA ? cuda_fail(cudaGetLastError(), "pipelined file path") : rc;
+        if (es != cudaSuccess) return cuda_fail(es, "cudaStreamSynchronize");
         return decode_status_word(*c->h_err, nullptr);
     }
+    if ((st2 = upload_all())) return st2;
     // general path: every slice uploaded on its own into a 256-byte aligned region
     size_t in_total = 0;
     std::vector<size_t> in_ofs(nimg), out_ofs(nimg);
@@ -246,7 +317,11 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
     return decode_status_word(*c->h_err, nullptr);
     };
     st = body();
-    if (gpu_crc) return finish_device_crc(c, s0, len - 77, h.data_crc16, st);
+    if (gpu_crc) {
+        const int su = upload_all();                     // an early return of the body must not skip the CRC: its verdict comes first
+        if (su) return su;
+        return finish_device_crc(c, s0, len - 77, h.data_crc16, st);
+    }
     return st;
 }
 

@@ -255,6 +255,17 @@ int b2bu_uastc_transcode_dev(int target, const void* d_blocks, size_t nbytes, si
 int b2bu_uastc_transcode_slices_dev(int target, const void* d_blocks, void* d_out, const b2bu_slice_dev* slices, uint32_t num_slices,
                                     void* d_status, void* stream)
 {
+    return uastc_transcode_slices_based(target, d_blocks, d_out, slices, num_slices, 0, d_status, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+
+namespace b2bu {
+
+// b2bu_uastc_transcode_slices_dev with the status-word block numbering starting at first_index
+int uastc_transcode_slices_based(int target, const void* d_blocks, void* d_out, const b2bu_slice_dev* slices, uint32_t num_slices,
+                                 uint64_t first_index, void* d_status, cudaStream_t stream)
+{
     if (target < B2BU_RGBA || target > B2BU_ETC2) return B2BU_ERR_ARGUMENT;
     if (num_slices == 0) return B2BU_OK;
     if (!d_blocks || !d_out || !slices || !d_status) return B2BU_ERR_ARGUMENT;
@@ -270,7 +281,7 @@ int b2bu_uastc_transcode_slices_dev(int target, const void* d_blocks, void* d_ou
     if (st) return st;
     const uint8_t* in = static_cast<const uint8_t*>(d_blocks);
     uint8_t* out = static_cast<uint8_t*>(d_out);
-    uint64_t base = 0;
+    uint64_t base = first_index;
     for (uint32_t i = 0; i < num_slices;) {
         // a run of slices that is one contiguous block array on both sides (RGBA output depends on the slice shape: no merging)
         uint64_t n = slices[i].nblocks;
@@ -284,13 +295,13 @@ int b2bu_uastc_transcode_slices_dev(int target, const void* d_blocks, void* d_ou
                 // that the tile kernel's bulk stores stay 16-byte aligned
                 skip = 1;
                 CK(launch_uastc_transcode(target, in + slices[i].in_ofs, out + slices[i].out_ofs, 1, 1u, base, reinterpret_cast<unsigned long long*>(d_status),
-                                          c->sm_count, reinterpret_cast<cudaStream_t>(stream)));
+                                          c->sm_count, stream));
                 count_launch(1);
             }
             if (n > skip) {
                 CK(launch_uastc_transcode(target, in + slices[i].in_ofs + skip * 16, out + slices[i].out_ofs + skip * ob, n - skip,
                                           slices[i].blocks_per_row ? slices[i].blocks_per_row : 1u, base + skip,
-                                          reinterpret_cast<unsigned long long*>(d_status), c->sm_count, reinterpret_cast<cudaStream_t>(stream)));
+                                          reinterpret_cast<unsigned long long*>(d_status), c->sm_count, stream));
                 count_launch(1);
             }
         }
@@ -299,6 +310,10 @@ int b2bu_uastc_transcode_slices_dev(int target, const void* d_blocks, void* d_ou
     }
     return B2BU_OK;
 }
+
+}  // namespace b2bu
+
+extern "C" {
 
 int b2bu_crc16_dev(const void* d_data, size_t len, uint16_t crc, uint16_t* result, void* stream)
 {

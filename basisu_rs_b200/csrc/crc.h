@@ -21,7 +21,8 @@ cudaError_t launch_crc16_partial(const void* d_data, uint64_t nchunks, uint64_t 
 
 // Whole message at any alignment: XORs sum_i r(piece_i) * x^(8 * bytes after piece i) over a head / 16 KiB chunks / tail
 // split into *d_acc (zeroed by the caller; up to three launches).  crc16_finish turns the sum into basis.rs's crc16(r, crc).
-cudaError_t launch_crc16_dev(const void* d_data, uint64_t len, uint32_t* d_acc, int sm_count, cudaStream_t stream);
+// bytes_after: bytes of the message that follow this piece (a message may be fed piece by piece, in any order).
+cudaError_t launch_crc16_dev(const void* d_data, uint64_t len, uint32_t* d_acc, int sm_count, cudaStream_t stream, uint64_t bytes_after = 0);
 uint16_t crc16_finish(uint32_t acc, uint64_t len, uint16_t crc);
 
 }  // namespace b2bu

@@ -130,19 +130,19 @@ static const CrcPowers& powers()
     return pw;
 }
 
-cudaError_t launch_crc16_dev(const void* d_data, uint64_t len, uint32_t* d_acc, int sm_count, cudaStream_t stream)
+cudaError_t launch_crc16_dev(const void* d_data, uint64_t len, uint32_t* d_acc, int sm_count, cudaStream_t stream, uint64_t bytes_after)
 {
     const uint8_t* p = static_cast<const uint8_t*>(d_data);
     uint64_t head = (16 - (reinterpret_cast<uintptr_t>(p) & 15)) & 15;
     if (head > len) head = len;
     const uint64_t nchunks = (len - head) / kCrcChunkBytes;
     const uint64_t tail = len - head - nchunks * kCrcChunkBytes;
-    if (head) crc16_small_kernel<<<1, 256, 0, stream>>>(p, (uint32_t)head, len - head, powers(), d_acc);
+    if (head) crc16_small_kernel<<<1, 256, 0, stream>>>(p, (uint32_t)head, len - head + bytes_after, powers(), d_acc);
     if (nchunks) {
         const uint64_t cap = (uint64_t)sm_count * 8;
-        crc16_partial_kernel<<<(unsigned)(nchunks < cap ? nchunks : cap), 256, 0, stream>>>(reinterpret_cast<const uint4*>(p + head), nchunks, tail, powers(), d_acc);
+        crc16_partial_kernel<<<(unsigned)(nchunks < cap ? nchunks : cap), 256, 0, stream>>>(reinterpret_cast<const uint4*>(p + head), nchunks, tail + bytes_after, powers(), d_acc);
     }
-    if (tail) crc16_small_kernel<<<1, 256, 0, stream>>>(p + head + nchunks * kCrcChunkBytes, (uint32_t)tail, 0, powers(), d_acc);
+    if (tail) crc16_small_kernel<<<1, 256, 0, stream>>>(p + head + nchunks * kCrcChunkBytes, (uint32_t)tail, bytes_after, powers(), d_acc);
     return cudaGetLastError();
 }
 

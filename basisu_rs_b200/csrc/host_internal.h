@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <mutex>
 #include <cuda_runtime.h>
+#include "../../include/b2bu.h"
 
 namespace b2bu {
 
@@ -44,5 +45,7 @@ int ensure(void** p, size_t* cap, size_t need);
 int cuda_fail(cudaError_t e, const char* what);
 int decode_status_word(unsigned long long w, uint64_t* first_bad);
 void count_launch(uint64_t n);
+int uastc_transcode_slices_based(int target, const void* d_blocks, void* d_out, const b2bu_slice_dev* slices, uint32_t num_slices,
+                                 uint64_t first_index, void* d_status, cudaStream_t stream);
 
 }  // namespace b2bu

@@ -332,3 +332,36 @@ def test_read_to_large_file_takes_the_device_crc_path(gpu_lib, oracle, pad):
     with pytest.raises(gpu_lib.BasisuError) as ei:
         gpu_lib.read_to_astc(bytes(g))
     assert str(ei.value) == "Data CRC16 failed"
+
+
+def test_read_to_pipelined_upload_of_a_multi_piece_file(gpu_lib, oracle):
+    """A 22 MB file: the upload is cut into 8 MiB pieces, the CRC is accumulated piece by piece and blocks are transcoded and
+    returned as soon as their bytes have arrived (RGBA: whole block rows).  Results, image table, error reporting."""
+    levels, blocks = _mip_chain(4096, seed=500)                   # 1024x1024 .. 1x1 blocks
+    slices = [dict(data=blocks[k].tobytes(), orig_width=max(1, 4096 >> k), orig_height=max(1, 4096 >> k), num_blocks_x=nb,
+                   num_blocks_y=nb, level_index=k, image_index=0) for k, nb in enumerate(levels)]
+    f = build_basis(slices, tex_format=1, total_images=1)
+    assert len(f) > 2 * (8 << 20)
+    for t, fn in ((2, gpu_lib.read_to_bc7), (3, gpu_lib.read_to_etc1), (0, lambda b: gpu_lib.read_to_rgba(b)[1])):
+        images = fn(f)
+        assert len(images) == len(levels)
+        for k, nb in enumerate(levels):
+            _, _, want = oracle_transcode(oracle, t, blocks[k], nb)
+            assert images[k].data == want.tobytes(), (t, k)
+    assert [im.data for im in gpu_lib.read_to_uastc(f)] == [b.tobytes() for b in blocks]
+    # an invalid block in the second piece (the file's CRC is computed over the damaged payload, so the CRC passes)
+    bad = [b.copy() for b in blocks]
+    bad[0][700000, 0] = 69
+    slices[0]["data"] = bad[0].tobytes()
+    g = build_basis(slices, tex_format=1, total_images=1)
+    with pytest.raises(gpu_lib.BasisuError) as ei:
+        gpu_lib.read_to_bc7(g)
+    assert str(ei.value) == "invalid mode index"
+    # a flipped bit anywhere: the CRC verdict comes first
+    g = bytearray(f); g[len(g) - 5] ^= 2
+    with pytest.raises(gpu_lib.BasisuError) as ei:
+        gpu_lib.read_to_etc1(bytes(g))
+    assert str(ei.value) == "Data CRC16 failed"
+    with pytest.raises(gpu_lib.BasisuError) as ei:
+        gpu_lib.read_to_uastc(bytes(g))
+    assert str(ei.value) == "Data CRC16 failed"
