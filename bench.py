@@ -50,6 +50,33 @@ def capture_stdout():
         os.dup2(2, 1)
 
 
+def bind_to_gpu_numa_node(device_index):
+    """One process per GPU: run this rank (and first-touch its pinned host buffers) on the CPU socket the GPU hangs off, so
+    that its H2D / D2H copies do not cross the socket interconnect.  Returns the NUMA node, or None when it cannot be found."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:                       # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def emit_line(line):
     sys.stdout.flush()
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
@@ -483,6 +510,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: basisu_rs_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
@@ -648,7 +676,8 @@ def main():
                          "int_bound": int_bound},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Gtexel/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * ob,
-                    "steps": args.e2e_steps, "launches": int(e2e_launches), "api": "b2bu_uastc_transcode (pinned host buffers)"},
+                    "steps": args.e2e_steps, "launches": int(e2e_launches), "api": "b2bu_uastc_transcode (pinned host buffers)",
+                    "host_numa_node_rank0": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "parity": {"device_vs_oracle_sample": parity, "e2e_vs_oracle_sample": e2e_parity},
