@@ -145,6 +145,9 @@ __device__ unsigned long long g_trace[160][64];
 #define B2BU_DMA_WAIT(bar, parity) mbar_wait((bar), (parity))
 #endif
 
+#ifndef B2BU_SORT_UNIFORM
+#define B2BU_SORT_UNIFORM 0     // measured: ASTC shuffled 55 -> 62 us, coherent 64 -> 62 us; off
+#endif
 #ifndef B2BU_SLOTS
 #define B2BU_SLOTS 2
 #endif
@@ -326,12 +329,36 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
             PH(1);
             {
                 // rank = old value of the warp's private counter (direct atomics: a MATCH.ANY / ballot + leader
-                // scheme measured 2-3x slower because each step waits for the previous atomic's round trip)
+                // scheme measured 2-3x slower because each step waits for the previous atomic's round trip).  Real
+                // textures are spatially coherent, and 32 consecutive blocks of one mode would be a 32-way same-address
+                // atomic: with B2BU_SORT_UNIFORM a warp whose 32 blocks agree adds 32 once and the shuffles that hand out
+                // the ranks run in the second pass -- it costs the mixed case more than it gains on runs, so it is off.
                 uint32_t rk[C::PERS];
+#if B2BU_SORT_UNIFORM
+                uint32_t unim = 0u;
+#pragma unroll
+                for (int j = 0; j < C::PERS; j++) {
+                    if (j < jmax) {
+                        const uint32_t m = mr[j];
+                        const bool uni = __all_sync(0xFFFFFFFFu, m == __shfl_sync(0xFFFFFFFFu, m, 0));
+                        unim |= (uni ? 1u : 0u) << j;
+                        rk[j] = 0u;
+                        if (!uni || lane == 0) rk[j] = atomicAdd(&mycnt[m], uni ? 32u : 1u);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < C::PERS; j++) {
+                    if (j < jmax) {
+                        if ((unim >> j) & 1u) rk[j] = __shfl_sync(0xFFFFFFFFu, rk[j], 0) + (uint32_t)lane;
+                        mr[j] |= rk[j] << 8;
+                    }
+                }
+#else
 #pragma unroll
                 for (int j = 0; j < C::PERS; j++) if (j < jmax) rk[j] = atomicAdd(&mycnt[mr[j]], 1u);
 #pragma unroll
                 for (int j = 0; j < C::PERS; j++) if (j < jmax) mr[j] |= rk[j] << 8;
+#endif
             }
             PH(2);
             named_bar_sync(1, C::SORT_THREADS);
