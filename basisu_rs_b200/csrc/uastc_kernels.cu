@@ -148,14 +148,21 @@ __device__ unsigned long long g_trace[160][64];
 #ifndef B2BU_SORT_UNIFORM
 #define B2BU_SORT_UNIFORM 0     // measured: ASTC shuffled 55 -> 62 us, coherent 64 -> 62 us; off
 #endif
+#ifndef B2BU_STAGGER
+#define B2BU_STAGGER 0
+#endif
 #ifndef B2BU_SLOTS
 #define B2BU_SLOTS 2
 #endif
+#ifndef B2BU_SLOTS16
+#define B2BU_SLOTS16 B2BU_SLOTS
+#endif
 
 template <int TARGET> struct PipeCfg {
-    static constexpr int NS = B2BU_SLOTS;                                   // tile slots in flight (load / sort / work / store)
     static constexpr int OB = TARGET == TGT_RGBA ? 64 : TARGET == TGT_ETC1 ? 8 : 16;
     static constexpr bool IN_PLACE = OB == 16;
+    // tile slots in flight (load / sort / work / store are four stages: a slot is busy through all of them)
+    static constexpr int NS = IN_PLACE ? B2BU_SLOTS16 : B2BU_SLOTS;
     static constexpr bool DYNAMIC = TARGET != TGT_ASTC;
     static constexpr int TILE = TARGET == TGT_RGBA ? B2BU_TILE_RGBA : TARGET == TGT_ETC1 ? B2BU_TILE_ETC1 : B2BU_TILE16;
     static constexpr int SORT_WARPS = B2BU_SORT_WARPS;
@@ -219,7 +226,11 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
     const uint32_t rlen = (uint32_t)(r1 - r0);
     // tile k covers [tile_start(k), tile_start(k + 1)) of the range.  The first two tiles are short (TILE/4, TILE/2)
     // so that the workers start early; the rest of the range is cut into equal tiles of at most TILE blocks.
-    const uint32_t a0 = rlen < (uint32_t)C::TILE / 4 ? rlen : (uint32_t)C::TILE / 4;
+    // B2BU_STAGGER: CTAs that start together stay in lockstep, so all 148 load at once, then all sort, all work, all store --
+    // every load and store runs at 1/148 of the HBM bandwidth and the memory system idles in between.  Different first-tile
+    // sizes put the CTAs at different phases of the tile period.
+    const uint32_t want0 = (uint32_t)C::TILE / 4 + (B2BU_STAGGER ? (blockIdx.x % (uint32_t)B2BU_STAGGER) * ((uint32_t)C::TILE * 3 / 4 / (uint32_t)(B2BU_STAGGER > 1 ? B2BU_STAGGER - 1 : 1)) & ~31u : 0u);
+    const uint32_t a0 = rlen < want0 ? rlen : want0;
     const uint32_t a1 = rlen - a0 < (uint32_t)C::TILE / 2 ? rlen - a0 : (uint32_t)C::TILE / 2;
     const uint32_t rest = rlen - a0 - a1;
     const uint32_t nrest = (rest + C::TILE - 1) / C::TILE;
@@ -443,7 +454,12 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
                 const uint4 b = tin[idx];
                 BlockOut o;
                 StridedRowSink sink{reinterpret_cast<uint4*>(tout) + idx, (uint64_t)C::TILE};     // RGBA: [4][TILE] pixel rows
+#ifdef B2BU_NULL_WORK      // tuning aid: the pipeline without the transcode (blocks are copied)
+                const uint32_t e = mode == 19u ? (uint32_t)ERR_MODE : (uint32_t)ERR_OK;
+                o.v = b; o.etc = make_uint2(b.x, b.y);
+#else
                 const uint32_t e = transcode_mode_sink<TARGET>(mode, b, T, o, sink);
+#endif
                 if (e != ERR_OK) {
                     report_error(err, index_base + base + idx, e);
                     o.v = make_uint4(0u, 0u, 0u, 0u); o.etc = make_uint2(0u, 0u);
