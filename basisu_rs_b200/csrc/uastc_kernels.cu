@@ -118,6 +118,15 @@ __constant__ uint8_t kBinOrder[32] = {3, 9, 16, 4, 7, 2, 12, 10, 11, 13, 14, 6, 
 #ifndef B2BU_TILE_ETC1
 #define B2BU_TILE_ETC1 B2BU_TILE16
 #endif
+// RGBA output straight from the worker threads to the image (four 16-byte row segments per block, scattered; the L2
+// merges the half-written 32-byte sectors) instead of through a [4][TILE] staging buffer and bulk stores: no 64 B per
+// block of staging, so the RGBA tile can be as large as the others.
+#ifndef B2BU_RGBA_DIRECT
+#define B2BU_RGBA_DIRECT 0
+#endif
+#ifndef B2BU_TILE_RGBA_DIRECT
+#define B2BU_TILE_RGBA_DIRECT 4096
+#endif
 #ifndef B2BU_SORT_WARPS
 #define B2BU_SORT_WARPS 8
 #endif
@@ -161,10 +170,11 @@ __device__ unsigned long long g_trace[160][64];
 template <int TARGET> struct PipeCfg {
     static constexpr int OB = TARGET == TGT_RGBA ? 64 : TARGET == TGT_ETC1 ? 8 : 16;
     static constexpr bool IN_PLACE = OB == 16;
+    static constexpr bool DIRECT = TARGET == TGT_RGBA && B2BU_RGBA_DIRECT;     // no staged output at all
     // tile slots in flight (load / sort / work / store are four stages: a slot is busy through all of them)
     static constexpr int NS = IN_PLACE ? B2BU_SLOTS16 : B2BU_SLOTS;
     static constexpr bool DYNAMIC = TARGET != TGT_ASTC;
-    static constexpr int TILE = TARGET == TGT_RGBA ? B2BU_TILE_RGBA : TARGET == TGT_ETC1 ? B2BU_TILE_ETC1 : B2BU_TILE16;
+    static constexpr int TILE = TARGET == TGT_RGBA ? (DIRECT ? B2BU_TILE_RGBA_DIRECT : B2BU_TILE_RGBA) : TARGET == TGT_ETC1 ? B2BU_TILE_ETC1 : B2BU_TILE16;
     static constexpr int SORT_WARPS = B2BU_SORT_WARPS;
     static constexpr int SORT_THREADS = SORT_WARPS * 32;
     static constexpr int WORK_WARPS = B2BU_WORK_WARPS;
@@ -174,7 +184,7 @@ template <int TARGET> struct PipeCfg {
     static constexpr int MAXITEMS = MAXORD / 32;
     static constexpr size_t OFF_IN = (TableBytes<TARGET>::value + 127) / 128 * 128;   // two slots
     static constexpr size_t OFF_OUT = OFF_IN + NS * (size_t)TILE * 16;                 // staging for ETC1 / RGBA, one per slot
-    static constexpr size_t OUT_SLOT = IN_PLACE ? 0 : (size_t)TILE * OB;
+    static constexpr size_t OUT_SLOT = (IN_PLACE || DIRECT) ? 0 : (size_t)TILE * OB;
     static constexpr size_t OFF_ORDER = OFF_OUT + NS * OUT_SLOT;
     static constexpr size_t OFF_INFO = OFF_ORDER + NS * (size_t)MAXORD * 2;
     static constexpr size_t OFF_WCNT = (OFF_INFO + NS * 32 * 4 + 15) / 16 * 16;
@@ -257,6 +267,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
         auto store_tile = [&](uint32_t k) {
             const uint32_t s = k % C::NS, nt = tile_blocks(k);
             const uint64_t g0 = r0 + tile_start(k);
+            if (C::DIRECT) return;                             // the workers have written the image themselves
             fence_async_smem();
             if (TARGET == TGT_RGBA) {
                 // four pixel rows per block row; a tile may span several block rows
@@ -454,6 +465,12 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
                 const uint4 b = tin[idx];
                 BlockOut o;
                 StridedRowSink sink{reinterpret_cast<uint4*>(tout) + idx, (uint64_t)C::TILE};     // RGBA: [4][TILE] pixel rows
+                if (C::DIRECT) {
+                    // uastc.rs:96-106: block (bx, by) of the row-major image, pitch 4 * blocks_per_row pixels (a device holds
+                    // fewer than 2^32 blocks of 80 bytes)
+                    const uint32_t gi = (uint32_t)(base + idx), by = gi / blocks_per_row, bx = gi - by * blocks_per_row;
+                    sink = StridedRowSink{reinterpret_cast<uint4*>(out) + (uint64_t)by * 4u * blocks_per_row + bx, (uint64_t)blocks_per_row};
+                }
 #ifdef B2BU_NULL_WORK      // tuning aid: the pipeline without the transcode (blocks are copied)
                 const uint32_t e = mode == 19u ? (uint32_t)ERR_MODE : (uint32_t)ERR_OK;
                 o.v = b; o.etc = make_uint2(b.x, b.y);
