@@ -48,7 +48,9 @@ constexpr uint32_t kTokErr = 1u << 31;            // tokenizer stopped here: cod
 enum { PH_PRED_SYM = 1, PH_PRED_CHECK = 2, PH_DELTA = 3, PH_SELECTOR = 4, PH_HISTORY = 5, PH_RANGE = 6 };
 
 struct alignas(16) PipeShared {
-    uint32_t ring[kRingWords];                    // compressed bytes of the slice (tokenizer)
+    // compressed bytes of the slice (tokenizer): four 1 KiB pieces, and the piece in slot 0 a second time behind them, so
+    // that the reader's address only has to wrap once per round (a round consumes less than one piece)
+    uint32_t ring[kRingWords + kHalfBytes / 4];
     uint2 tok[kTokRounds][kRound];                // tokenizer -> resolver
     uint16_t hist[64];                            // selector history when it fits (it always does for real files)
     uint64_t bar_full[kTokRounds], bar_empty[kTokRounds];
@@ -59,35 +61,35 @@ struct alignas(16) PipeShared {
 // word as it was before the last refill.  Reads take at most 16 bits and every read is followed by a refill to >= 32
 // bits, so `pre` always holds >= 16 valid bits and the next table index can be formed from it without waiting for the
 // refill (which then sits beside the dependent chain, not on it).
-struct BitState { uint32_t lo, hi, pre; int avail; uint32_t nw, nextw; };       // nextw: absolute word index in the slice
+// x: bits still buffered in its low 8 bits (<= 64), garbage above; raddr: shared address of the ring word after nw
+struct BitState { uint32_t lo, hi, pre, x, nw, raddr; };
 
-// Drops e & 31 (<= 16) bits and refills.  Written as predicated PTX so that the refill is straight-line code (the
-// compiler's version of the same C++ is a branch with a convergence barrier around it on every symbol).
-__device__ __forceinline__ void bits_consume(BitState& s, uint32_t e, uint32_t ring_base)      // ring_base: shared address of the ring
+// Drops `e & 31` (<= 16) bits and refills; bits 5-7 of e must be zero (callers strip flags / symbol bits that sit there).
+// Written as predicated PTX so that the refill is straight-line code (the compiler's version of the same C++ is a branch
+// with a convergence barrier around it on every symbol) and kept to 11 instructions: the bit count is updated by
+// subtracting the whole table entry (the symbol in bits 8+ only disturbs bits the count does not use), the shifts take
+// their amounts modulo 32 straight from that register, and the ring address is a plain running pointer.
+__device__ __forceinline__ void bits_consume(BitState& s, uint32_t e)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        ".reg .u32 len, sh, a;\n"
+        ".reg .u32 sh, t;\n"
         "shf.r.wrap.b32 %0, %0, %1, %6;\n"                   // lo = (hi:lo) >> len
         "shf.r.wrap.b32 %1, %1, 0, %6;\n"                    // hi >>= len
-        "and.b32 len, %6, 31;\n"
-        "sub.s32 %3, %3, len;\n"
+        "sub.u32 %3, %3, %6;\n"                              // count -= len
         "mov.b32 %2, %0;\n"                                  // pre = lo
-        "setp.lt.s32 p, %3, 32;\n"                           // avail is in [16, 31] when the refill happens
-        "shl.b32 sh, %4, %3;\n"
+        "and.b32 t, %3, 0xE0;\n"
+        "setp.eq.u32 p, t, 0;\n"                             // count < 32 (it is >= 16 here)
+        "shf.l.wrap.b32 sh, 0, %4, %3;\n"                    // nw << count
         "@p or.b32 %0, %0, sh;\n"
-        "sub.s32 a, 32, %3;\n"
-        "@p shr.u32 %1, %4, a;\n"
-        "@p add.s32 %3, %3, 32;\n"
-        "and.b32 a, %5, %8;\n"
-        "shl.b32 a, a, 2;\n"
-        "add.u32 a, a, %7;\n"
-        "@p ld.shared.u32 %4, [a];\n"
-        "@p add.u32 %5, %5, 1;\n"
+        "@p shf.l.wrap.b32 %1, %4, 0, %3;\n"                 // hi = nw >> (32 - count)
+        "@p add.u32 %3, %3, 32;\n"
+        "@p ld.shared.u32 %4, [%5];\n"
+        "@p add.u32 %5, %5, 4;\n"
         "}\n"
-        : "+r"(s.lo), "+r"(s.hi), "=r"(s.pre), "+r"(s.avail), "+r"(s.nw), "+r"(s.nextw)
-        : "r"(e), "r"(ring_base), "n"(kRingWords - 1)
+        : "+r"(s.lo), "+r"(s.hi), "=r"(s.pre), "+r"(s.x), "+r"(s.nw), "+r"(s.raddr)
+        : "r"(e)
         : "memory");
 }
 
@@ -95,25 +97,25 @@ __device__ __forceinline__ void bits_consume(BitState& s, uint32_t e, uint32_t r
 struct SlowSym { BitState bs; uint32_t sym; };
 // huffman.rs:186-198 for a first-level entry flagged `special`: a run symbol (already consumed) or a code longer than the
 // first-level table, which is looked up in the reference's flat table in global memory.  sym = 0xFFFFFFFF: no code matches.
-__device__ __noinline__ SlowSym huff_slow(BitState bs, uint32_t ring_base, uint32_t e, const uint32_t* __restrict__ flat, uint32_t max_len)
+__device__ __noinline__ SlowSym huff_slow(BitState bs, uint32_t e, const uint32_t* __restrict__ flat, uint32_t max_len)
 {
     SlowSym r;
     if ((e & 31u) != 0u) { r.bs = bs; r.sym = e >> 8; return r; }
     const uint32_t f = __ldg(flat + (bs.lo & ((1u << max_len) - 1u)));
     if ((f & 31u) == 0u) { r.bs = bs; r.sym = 0xFFFFFFFFu; return r; }
-    bits_consume(bs, f, ring_base);
+    bits_consume(bs, f & 31u);
     r.bs = bs; r.sym = f >> 5;
     return r;
 }
 
 // mod.rs:585-608 decode_vlc.  sym = the value, or 0xFFFFFFFF when the reference would panic (ofs >= 32).
-__device__ __noinline__ SlowSym vlc_decode(BitState bs, uint32_t ring_base, uint32_t chunk_bits)
+__device__ __noinline__ SlowSym vlc_decode(BitState bs, uint32_t chunk_bits)
 {
     SlowSym r;
     uint32_t v = 0, ofs = 0;
     for (;;) {
         const uint32_t c = bs.lo & ((2u << chunk_bits) - 1u);
-        bits_consume(bs, chunk_bits + 1u, ring_base);
+        bits_consume(bs, chunk_bits + 1u);
         v |= (c & ((1u << chunk_bits) - 1u)) << ofs;
         ofs += chunk_bits;
         if ((c >> chunk_bits) == 0u) break;
@@ -142,6 +144,11 @@ __device__ __forceinline__ void piece_store(uint32_t* ring, uint32_t piece, int 
     uint4* dst = reinterpret_cast<uint4*>(ring + (piece % kRingHalves) * (kHalfBytes / 4));
     dst[lane] = r[0];
     dst[lane + 32] = r[1];
+    if (piece % kRingHalves == 0u) {                          // slot 0 is mirrored behind the ring
+        uint4* mir = reinterpret_cast<uint4*>(ring + kRingWords);
+        mir[lane] = r[0];
+        mir[lane + 32] = r[1];
+    }
 }
 
 #ifdef B2BU_K2_TRACE
@@ -199,14 +206,14 @@ __device__ __noinline__ TokState pair_slow(TokState st, const TokConsts K, const
         if (st.pred_rep != 0u) { st.pred_rep--; cur = st.prev_sym; }
         else {
             const uint32_t e = lds_u32(K.t0 + ((bs.pre & K.m0) << 2));
-            bits_consume(bs, e, K.ring_base);
+            bits_consume(bs, e & ~kL1Special);
             cur = e >> 8;
             if (e & kL1Special) {
-                SlowSym r = huff_slow(bs, K.ring_base, e, P.flat[0], P.max_len[0]);
+                SlowSym r = huff_slow(bs, e, P.flat[0], P.max_len[0]);
                 bs = r.bs; cur = r.sym;
                 if (cur == 0xFFFFFFFFu) terr = ETC1S_ERR_HUFFMAN | (PH_PRED_SYM << 4);
                 else if (cur == 256u) {                                           // mod.rs:268-275: run of the previous symbol
-                    r = vlc_decode(bs, K.ring_base, 4);
+                    r = vlc_decode(bs, 4);
                     bs = r.bs;
                     if (r.sym == 0xFFFFFFFFu) terr = ETC1S_ERR_VLC | (PH_PRED_SYM << 4);
                     st.pred_rep = r.sym + 3u - 1u;
@@ -223,10 +230,10 @@ __device__ __noinline__ TokState pair_slow(TokState st, const TokConsts K, const
         uint32_t d = 0u, tokA = pred << 16;
         if (pred == 3u) {                                                         // mod.rs:340-353: DPCM delta symbol
             const uint32_t e = lds_u32(K.t1 + ((bs.pre & K.m1) << 2));
-            bits_consume(bs, e, K.ring_base);
+            bits_consume(bs, e & ~kL1Special);
             d = e >> 8;
             if (e & kL1Special) {
-                const SlowSym r = huff_slow(bs, K.ring_base, e, P.flat[1], P.max_len[1]);
+                const SlowSym r = huff_slow(bs, e, P.flat[1], P.max_len[1]);
                 bs = r.bs; d = r.sym;
                 if (d == 0xFFFFFFFFu) terr = ETC1S_ERR_HUFFMAN | (PH_DELTA << 4);
             }
@@ -236,21 +243,21 @@ __device__ __noinline__ TokState pair_slow(TokState st, const TokConsts K, const
         else if (st.sel_rle > 0u) { st.sel_rle--; tokA |= K.num_selectors; }      // mod.rs:370-372
         else {
             const uint32_t e = lds_u32(K.t2 + ((bs.pre & K.m2) << 2));
-            bits_consume(bs, e, K.ring_base);
+            bits_consume(bs, e & ~kL1Special);
             uint32_t sym = e >> 8;
             if (e & kL1Special) {
-                SlowSym r = huff_slow(bs, K.ring_base, e, P.flat[2], P.max_len[2]);
+                SlowSym r = huff_slow(bs, e, P.flat[2], P.max_len[2]);
                 bs = r.bs; sym = r.sym;
                 if (sym == 0xFFFFFFFFu) terr = ETC1S_ERR_HUFFMAN | (PH_SELECTOR << 4);
                 else if (sym == K.rle_sym) {                                      // mod.rs:378-396
                     const uint32_t e3 = lds_u32(K.t3 + ((bs.pre & K.m3) << 2));
-                    bits_consume(bs, e3, K.ring_base);
+                    bits_consume(bs, e3 & ~kL1Special);
                     uint32_t cnt = e3 >> 8;
-                    if (e3 & kL1Special) { r = huff_slow(bs, K.ring_base, e3, P.flat[3], P.max_len[3]); bs = r.bs; cnt = r.sym; }
+                    if (e3 & kL1Special) { r = huff_slow(bs, e3, P.flat[3], P.max_len[3]); bs = r.bs; cnt = r.sym; }
                     if (cnt == 0xFFFFFFFFu) terr = ETC1S_ERR_HUFFMAN | (PH_SELECTOR << 4);
                     else {
                         if (cnt == 63u) {
-                            r = vlc_decode(bs, K.ring_base, 7);
+                            r = vlc_decode(bs, 7);
                             bs = r.bs; cnt = r.sym;
                             if (cnt == 0xFFFFFFFFu) terr = ETC1S_ERR_VLC | (PH_SELECTOR << 4);
                         }
@@ -283,7 +290,7 @@ __device__ __forceinline__ bool fast_pairs(TokState& st, const TokConsts& K, uin
         if (EVEN) {
             const uint32_t rep = pred_rep != 0u ? 1u : 0u;
             const uint32_t e0 = lds_u32_if(K.t0 + ((bs.pre & K.m0) << 2), rep ^ 1u);
-            bits_consume(bs, e0, K.ring_base);
+            bits_consume(bs, e0);
             spec |= e0;
             cur = rep ? prev_sym : ((e0 >> 8) & 0xFFu);
             pred_rep -= rep;
@@ -294,10 +301,10 @@ __device__ __forceinline__ bool fast_pairs(TokState& st, const TokConsts& K, uin
         for (int j = 0; j < 2; j++) {
             const uint32_t pred = (cur >> (2 * j)) & 3u;
             const uint32_t e1 = lds_u32_if(K.t1 + ((bs.pre & K.m1) << 2), pred == 3u ? 1u : 0u);
-            bits_consume(bs, e1, K.ring_base);
+            bits_consume(bs, e1);
             const uint32_t run = sel_rle != 0u ? 1u : 0u;
             const uint32_t e2 = lds_u32_if(K.t2 + ((bs.pre & K.m2) << 2), run ^ 1u);
-            bits_consume(bs, e2, K.ring_base);
+            bits_consume(bs, e2);
             spec |= e1 | e2;
             sel_rle -= run;
             t[2 * q + j] = make_uint2((run ? K.num_selectors : (e2 >> 8)) | (pred << 16), e1 >> 8);
@@ -338,7 +345,8 @@ static __device__ void etc1s_tokenize(const Etc1sDecodeParams& P, const Etc1sSli
     __syncwarp();
 
     TokState st;
-    st.bs.lo = ring[0]; st.bs.hi = ring[1]; st.bs.pre = st.bs.lo; st.bs.avail = 64; st.bs.nw = ring[2]; st.bs.nextw = 3;
+    st.bs.lo = ring[0]; st.bs.hi = ring[1]; st.bs.pre = st.bs.lo; st.bs.x = 64u; st.bs.nw = ring[2]; st.bs.raddr = K.ring_base + 12u;
+    uint32_t lap_bytes = 0;                       // slice byte offset of the ring's first slot in the reader's current lap
     st.sel_rle = 0; st.pred_rep = 0; st.prev_sym = 0; st.cur = 0; st.terr = 0;
     uint32_t round = 0;
     K2T_DECL(const long long tt0 = clock64(); uint32_t n_slow = 0; uint32_t n_sym = 0; long long t_wait = 0;)
@@ -356,7 +364,8 @@ static __device__ void etc1s_tokenize(const Etc1sDecodeParams& P, const Etc1sSli
             }
             // start fetching the next ring piece if the reader is about to need it: pieces up to pos+2 must be resident
             // before the next round starts
-            const uint32_t pos = (st.bs.nextw * 4u) / kHalfBytes;
+            if (st.bs.raddr >= K.ring_base + (uint32_t)kRingWords * 4u) { st.bs.raddr -= (uint32_t)kRingWords * 4u; lap_bytes += (uint32_t)kRingWords * 4u; }
+            const uint32_t pos = (lap_bytes + (st.bs.raddr - K.ring_base)) / kHalfBytes;
             const bool fetch = loaded < pos + 3u;                                 // warp-uniform
             uint4 pre[2];
             if (fetch) piece_load(data, job.data_len, loaded, lane, pre);
