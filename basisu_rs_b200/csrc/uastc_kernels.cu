@@ -157,6 +157,9 @@ __device__ unsigned long long g_trace[160][64];
 #ifndef B2BU_SORT_UNIFORM
 #define B2BU_SORT_UNIFORM 0     // measured: ASTC shuffled 55 -> 62 us, coherent 64 -> 62 us; off
 #endif
+#ifndef B2BU_CTAS_PER_SM
+#define B2BU_CTAS_PER_SM 1      // persistent CTAs per SM; 2 x 512 threads with half-size tiles measured 72 us (ASTC) against 55
+#endif
 #ifndef B2BU_STAGGER
 #define B2BU_STAGGER 0
 #endif
@@ -205,7 +208,7 @@ __device__ __forceinline__ uint64_t cta_range_start(uint64_t nblocks, uint64_t q
 }
 
 template <int TARGET>
-__global__ void __launch_bounds__(PipeCfg<TARGET>::THREADS, 1)
+__global__ void __launch_bounds__(PipeCfg<TARGET>::THREADS, B2BU_CTAS_PER_SM)
 uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64_t nblocks, uint32_t blocks_per_row,
                     uint64_t index_base, unsigned long long* __restrict__ err, uint64_t range_quot, uint32_t range_rem)
 {
@@ -512,7 +515,8 @@ static cudaError_t launch_sorted(const uint4* in, void* d_out, uint64_t nblocks,
     }
     // one persistent CTA per SM; fewer when the input is small (at least ~one half tile each)
     const uint64_t want = (nblocks + C::TILE / 2 - 1) / (C::TILE / 2);
-    const unsigned grid = (unsigned)(want < (uint64_t)sm_count ? want : (uint64_t)sm_count);
+    const uint64_t cap = (uint64_t)sm_count * B2BU_CTAS_PER_SM;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
     uastc_sorted_kernel<TARGET><<<grid, C::THREADS, C::SMEM, stream>>>(in, d_out, nblocks, bpr, index_base, d_err, nblocks / grid, (uint32_t)(nblocks % grid));
     return cudaGetLastError();
 }
