@@ -212,8 +212,10 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": "Gtexels/s UASTC->%s" % args.target.upper(), "value": value, "unit": "Gtexel/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "UASTC->%s 8192x8192 (%d blocks/step), CPU port on a bounded sample" % (args.target.upper(), args.blocks),
-                   "payload": args.payload, "sample_blocks": n},
+        # the b200 arm's workload and payload (same strings); the bounded sample a step covers is described in cpu_baseline.sample
+        "config": {"workload": "UASTC->%s 4x4 transcode, synthetic 8192x8192 texture (%d blocks) per GPU per step"
+                               % (args.target.upper(), args.blocks),
+                   "payload": args.payload + " (reference KAT blocks tiled/permuted, seed = rank)", "sample_blocks": n},
         "cpu_baseline": {"value": value, "unit": "Gtexel/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Gtexel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
