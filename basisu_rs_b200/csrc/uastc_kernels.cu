@@ -157,6 +157,9 @@ __device__ unsigned long long g_trace[160][64];
 #ifndef B2BU_SORT_UNIFORM
 #define B2BU_SORT_UNIFORM 0     // measured: ASTC shuffled 55 -> 62 us, coherent 64 -> 62 us; off
 #endif
+#ifndef B2BU_SORT_SPREAD
+#define B2BU_SORT_SPREAD 1
+#endif
 #ifndef B2BU_CTAS_PER_SM
 #define B2BU_CTAS_PER_SM 1      // persistent CTAs per SM; 2 x 512 threads with half-size tiles measured 72 us (ASTC) against 55
 #endif
@@ -319,6 +322,10 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
     if (warp >= C::WORK_WARPS) {
         // ================================ sorter warps ================================
         const int sw = warp - C::WORK_WARPS, st = sw * 32 + lane;
+        // block of sorter thread st inside each run of SORT_THREADS blocks.  Real textures have runs of one mode, and 32
+        // consecutive blocks of one mode under one warp instruction are a 32-way same-address atomic: B2BU_SORT_SPREAD
+        // puts the lanes of a warp 9 blocks apart (a bijection on 0..255; the 16-byte stride keeps the 4-way bank pattern).
+        const int bst = (B2BU_SORT_SPREAD && (C::SORT_THREADS & (C::SORT_THREADS - 1)) == 0) ? ((st * 9) & (C::SORT_THREADS - 1)) : st;
         uint32_t* mycnt = wcnt + sw * 32;
         for (uint32_t k = 0; k < ntiles; k++) {
             const uint32_t s = k % C::NS, u = k / C::NS, nt = tile_blocks(k);
@@ -342,13 +349,13 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
             for (int j = 0; j < C::PERS; j++) {
                 // blocks past the end of a short tile read stale slot contents (always inside the slot); they are discarded below
                 mr[j] = 31u;
-                if (j < jmax) mr[j] = tin[st + j * C::SORT_THREADS].x & 127u;
+                if (j < jmax) mr[j] = tin[bst + j * C::SORT_THREADS].x & 127u;
             }
 #pragma unroll
             for (int j = 0; j < C::PERS; j++) {
                 if (j < jmax) {
                     const uint32_t lut = T.mode_lut[mr[j]];
-                    mr[j] = (uint32_t)(st + j * C::SORT_THREADS) < nt ? lut : 31u;     // 31 = unused bin
+                    mr[j] = (uint32_t)(bst + j * C::SORT_THREADS) < nt ? lut : 31u;     // 31 = unused bin
                 }
             }
             PH(1);
@@ -420,7 +427,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
                 for (int j = 0; j < C::PERS; j++) if (j < jmax) bs[j] = mybase[mr[j] & 0xFFu];
 #pragma unroll
                 for (int j = 0; j < C::PERS; j++)
-                    if (j < jmax && (mr[j] & 0xFFu) < (uint32_t)kBins) ord[bs[j] + (mr[j] >> 8)] = (uint16_t)(st + j * C::SORT_THREADS);
+                    if (j < jmax && (mr[j] & 0xFFu) < (uint32_t)kBins) ord[bs[j] + (mr[j] >> 8)] = (uint16_t)(bst + j * C::SORT_THREADS);
             }
             PH(6);
             named_bar_sync(1, C::SORT_THREADS);
