@@ -1,0 +1,33 @@
+// Tuning aid: latency of a dependent chain through shared-memory loads for one warp, with the load (a) always executed,
+// (b) predicated off, (c) absent -- does a predicated-off LDS still cost its consumer the load latency?
+#include <cstdio>
+#include <cuda_runtime.h>
+__global__ void probe(unsigned* out, int iters, int mode)
+{
+    __shared__ unsigned tab[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) tab[i] = (i * 7u + 3u) & 1023u;
+    __syncthreads();
+    unsigned x = threadIdx.x & 0u, on = mode == 0 ? 1u : 0u;
+    const unsigned base = (unsigned)__cvta_generic_to_shared(tab);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            unsigned e = 0;
+            if (mode < 2) asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\nmov.u32 %0, 0;\n@p ld.shared.u32 %0, [%1];\n}\n" : "=r"(e) : "r"(base + ((x & 1023u) << 2)), "r"(on));
+            x = (x + e + 1u) & 1023u;           // dependent on the (possibly skipped) load
+        }
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) { out[0] = x; out[1] = (unsigned)((t1 - t0) / (iters * 8)); }
+}
+int main()
+{
+    unsigned* d; cudaMalloc(&d, 8);
+    for (int mode = 0; mode < 3; mode++) {
+        probe<<<1, 32>>>(d, 20000, mode);
+        unsigned h[2]; cudaMemcpy(h, d, 8, cudaMemcpyDeviceToHost);
+        printf("%s: %u cycles per link\n", mode == 0 ? "LDS executed" : mode == 1 ? "LDS predicated off" : "no LDS", h[1]);
+    }
+    return 0;
+}
