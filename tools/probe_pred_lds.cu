@@ -14,7 +14,11 @@ __global__ void probe(unsigned* out, int iters, int mode)
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             unsigned e = 0;
-            if (mode < 2) asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\nmov.u32 %0, 0;\n@p ld.shared.u32 %0, [%1];\n}\n" : "=r"(e) : "r"(base + ((x & 1023u) << 2)), "r"(on));
+            if (mode == 3) {                     // a warp-uniform, data-dependent branch around the load (taken about half the time)
+                if (x & 1u) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(base + ((x & 1023u) << 2)));
+            } else if (mode == 4) {              // the same branch with nothing inside but an ALU op
+                if (x & 1u) asm volatile("add.u32 %0, %1, 5;" : "=r"(e) : "r"(x));
+            } else if (mode < 2) asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\nmov.u32 %0, 0;\n@p ld.shared.u32 %0, [%1];\n}\n" : "=r"(e) : "r"(base + ((x & 1023u) << 2)), "r"(on));
             x = (x + e + 1u) & 1023u;           // dependent on the (possibly skipped) load
         }
     }
@@ -24,10 +28,10 @@ __global__ void probe(unsigned* out, int iters, int mode)
 int main()
 {
     unsigned* d; cudaMalloc(&d, 8);
-    for (int mode = 0; mode < 3; mode++) {
+    for (int mode = 0; mode < 5; mode++) {
         probe<<<1, 32>>>(d, 20000, mode);
         unsigned h[2]; cudaMemcpy(h, d, 8, cudaMemcpyDeviceToHost);
-        printf("%s: %u cycles per link\n", mode == 0 ? "LDS executed" : mode == 1 ? "LDS predicated off" : "no LDS", h[1]);
+        printf("%s: %u cycles per link\n", mode == 0 ? "LDS executed" : mode == 1 ? "LDS predicated off" : mode == 2 ? "no LDS" : mode == 3 ? "LDS under a uniform branch (about half taken)" : "uniform branch around an ALU op", h[1]);
     }
     return 0;
 }
