@@ -18,6 +18,8 @@ __global__ void probe(unsigned* out, int iters, int mode)
                 if (x & 1u) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(base + ((x & 1023u) << 2)));
             } else if (mode == 4) {              // the same branch with nothing inside but an ALU op
                 if (x & 1u) asm volatile("add.u32 %0, %1, 5;" : "=r"(e) : "r"(x));
+            } else if (mode == 5) {              // load AND its consumer predicated off: does the consumer still wait for the load's scoreboard?
+                asm volatile("{\n.reg .pred p;\n.reg .u32 t;\nsetp.ne.u32 p, %2, 0;\n@p ld.shared.u32 t, [%1];\n@p add.u32 %0, %0, t;\n}\n" : "+r"(x) : "r"(base + ((x & 1023u) << 2)), "r"(on));
             } else if (mode < 2) asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\nmov.u32 %0, 0;\n@p ld.shared.u32 %0, [%1];\n}\n" : "=r"(e) : "r"(base + ((x & 1023u) << 2)), "r"(on));
             x = (x + e + 1u) & 1023u;           // dependent on the (possibly skipped) load
         }
@@ -28,10 +30,10 @@ __global__ void probe(unsigned* out, int iters, int mode)
 int main()
 {
     unsigned* d; cudaMalloc(&d, 8);
-    for (int mode = 0; mode < 5; mode++) {
+    for (int mode = 0; mode < 6; mode++) {
         probe<<<1, 32>>>(d, 20000, mode);
         unsigned h[2]; cudaMemcpy(h, d, 8, cudaMemcpyDeviceToHost);
-        printf("%s: %u cycles per link\n", mode == 0 ? "LDS executed" : mode == 1 ? "LDS predicated off" : mode == 2 ? "no LDS" : mode == 3 ? "LDS under a uniform branch (about half taken)" : "uniform branch around an ALU op", h[1]);
+        printf("%s: %u cycles per link\n", mode == 0 ? "LDS executed" : mode == 1 ? "LDS predicated off" : mode == 2 ? "no LDS" : mode == 3 ? "LDS under a uniform branch (about half taken)" : mode == 4 ? "uniform branch around an ALU op" : "LDS and its consumer both predicated off", h[1]);
     }
     return 0;
 }
