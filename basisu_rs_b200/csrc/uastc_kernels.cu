@@ -157,6 +157,9 @@ __device__ unsigned long long g_trace[160][64];
 #ifndef B2BU_SORT_UNIFORM
 #define B2BU_SORT_UNIFORM 0     // measured: ASTC shuffled 55 -> 62 us, coherent 64 -> 62 us; off
 #endif
+#ifndef B2BU_STATIC_BC7
+#define B2BU_STATIC_BC7 0
+#endif
 #ifndef B2BU_SORT_SPREAD
 #define B2BU_SORT_SPREAD 1
 #endif
@@ -179,7 +182,7 @@ template <int TARGET> struct PipeCfg {
     static constexpr bool DIRECT = TARGET == TGT_RGBA && B2BU_RGBA_DIRECT;     // no staged output at all
     // tile slots in flight (load / sort / work / store are four stages: a slot is busy through all of them)
     static constexpr int NS = IN_PLACE ? B2BU_SLOTS16 : B2BU_SLOTS;
-    static constexpr bool DYNAMIC = TARGET != TGT_ASTC;
+    static constexpr bool DYNAMIC = B2BU_STATIC_BC7 ? (TARGET != TGT_ASTC && TARGET != TGT_BC7) : TARGET != TGT_ASTC;
     static constexpr int TILE = TARGET == TGT_RGBA ? (DIRECT ? B2BU_TILE_RGBA_DIRECT : B2BU_TILE_RGBA) : TARGET == TGT_ETC1 ? B2BU_TILE_ETC1 : B2BU_TILE16;
     static constexpr int SORT_WARPS = B2BU_SORT_WARPS;
     static constexpr int SORT_THREADS = SORT_WARPS * 32;
