@@ -430,6 +430,16 @@ struct StridedRowSink {                    // rows `stride` uint4 apart (shared 
     B2BU_DI void row(int y, const uint4& v) { p[(uint64_t)y * stride] = v; }
 };
 
+// Tile staging of the RGBA kernel: pixel row 0 of a block replaces the block's own 16 input bytes (the thread has read them),
+// rows 1-3 go to a [3][stride] array -- 48 instead of 64 staged bytes per block, so a tile holds a third more blocks.
+struct TileRowSink {
+    static constexpr bool ROLLED = true;
+    uint4* row0;
+    uint4* rows123;
+    uint64_t stride;
+    B2BU_DI void row(int y, const uint4& v) { if (y == 0) *row0 = v; else rows123[(uint64_t)(y - 1) * stride] = v; }
+};
+
 template <bool MULTI, bool DUAL, class Sink> B2BU_DI void interp_rows(Canon& c, Sink& sink)
 {
     if (Sink::ROLLED) {

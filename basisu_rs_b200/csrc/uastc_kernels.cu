@@ -113,7 +113,7 @@ __constant__ uint8_t kBinOrder[32] = {3, 9, 16, 4, 7, 2, 12, 10, 11, 13, 14, 6, 
 #define B2BU_TILE16 4096
 #endif
 #ifndef B2BU_TILE_RGBA
-#define B2BU_TILE_RGBA 1344     // as large as two slots of 80 B per block fit: 1024 -> 1344 took RGBA from 152 to 131 us
+#define B2BU_TILE_RGBA 1536     // 64 B of shared memory per block and slot; 1024 -> 1344 -> 1536 blocks: RGBA 152 -> 131 -> 122 us (1664: 124)
 #endif
 #ifndef B2BU_TILE_ETC1
 #define B2BU_TILE_ETC1 B2BU_TILE16
@@ -193,7 +193,8 @@ template <int TARGET> struct PipeCfg {
     static constexpr int MAXITEMS = MAXORD / 32;
     static constexpr size_t OFF_IN = (TableBytes<TARGET>::value + 127) / 128 * 128;   // two slots
     static constexpr size_t OFF_OUT = OFF_IN + NS * (size_t)TILE * 16;                 // staging for ETC1 / RGBA, one per slot
-    static constexpr size_t OUT_SLOT = (IN_PLACE || DIRECT) ? 0 : (size_t)TILE * OB;
+    // RGBA stages 48 B per block: pixel row 0 goes where the block's input was (TileRowSink)
+    static constexpr size_t OUT_SLOT = (IN_PLACE || DIRECT) ? 0 : TARGET == TGT_RGBA ? (size_t)TILE * 48 : (size_t)TILE * OB;
     static constexpr size_t OFF_ORDER = OFF_OUT + NS * OUT_SLOT;
     static constexpr size_t OFF_INFO = OFF_ORDER + NS * (size_t)MAXORD * 2;
     static constexpr size_t OFF_WCNT = (OFF_INFO + NS * 32 * 4 + 15) / 16 * 16;
@@ -280,7 +281,8 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
             fence_async_smem();
             if (TARGET == TGT_RGBA) {
                 // four pixel rows per block row; a tile may span several block rows
-                const uint4* src = reinterpret_cast<const uint4*>(out_s + s * C::OUT_SLOT);   // [4][TILE]
+                const uint4* src123 = reinterpret_cast<const uint4*>(out_s + s * C::OUT_SLOT);   // pixel rows 1-3: [3][TILE]
+                const uint4* src0 = in_s + s * C::TILE;                                            // pixel row 0: in place
                 uint32_t i = 0;
                 uint64_t by = g0 / blocks_per_row;
                 uint32_t bx = (uint32_t)(g0 - by * blocks_per_row);
@@ -288,7 +290,8 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
                     const uint32_t seg = nt - i < blocks_per_row - bx ? nt - i : blocks_per_row - bx;
 #pragma unroll
                     for (int y = 0; y < 4; y++)
-                        tma_store_1d_nocommit(reinterpret_cast<uint4*>(out) + (by * 4 + y) * blocks_per_row + bx, src + y * C::TILE + i, seg * 16u);
+                        tma_store_1d_nocommit(reinterpret_cast<uint4*>(out) + (by * 4 + y) * blocks_per_row + bx,
+                                              (y == 0 ? src0 : src123 + (y - 1) * C::TILE) + i, seg * 16u);
                     i += seg; bx = 0; by++;
                 }
             } else if (TARGET == TGT_ETC1) {
@@ -477,12 +480,13 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
                 const uint32_t idx = ord[item * 32 + lane];
                 const uint4 b = tin[idx];
                 BlockOut o;
-                StridedRowSink sink{reinterpret_cast<uint4*>(tout) + idx, (uint64_t)C::TILE};     // RGBA: [4][TILE] pixel rows
+                TileRowSink sink{tin + idx, reinterpret_cast<uint4*>(tout) + idx, (uint64_t)C::TILE};
                 if (C::DIRECT) {
                     // uastc.rs:96-106: block (bx, by) of the row-major image, pitch 4 * blocks_per_row pixels (a device holds
                     // fewer than 2^32 blocks of 80 bytes)
                     const uint32_t gi = (uint32_t)(base + idx), by = gi / blocks_per_row, bx = gi - by * blocks_per_row;
-                    sink = StridedRowSink{reinterpret_cast<uint4*>(out) + (uint64_t)by * 4u * blocks_per_row + bx, (uint64_t)blocks_per_row};
+                    uint4* g = reinterpret_cast<uint4*>(out) + (uint64_t)by * 4u * blocks_per_row + bx;
+                    sink = TileRowSink{g, g + blocks_per_row, (uint64_t)blocks_per_row};
                 }
 #ifdef B2BU_NULL_WORK      // tuning aid: the pipeline without the transcode (blocks are copied)
                 const uint32_t e = mode == 19u ? (uint32_t)ERR_MODE : (uint32_t)ERR_OK;
