@@ -283,11 +283,13 @@ int uastc_transcode_slices_based(int target, const void* d_blocks, void* d_out, 
     uint8_t* out = static_cast<uint8_t*>(d_out);
     uint64_t base = first_index;
     for (uint32_t i = 0; i < num_slices;) {
-        // a run of slices that is one contiguous block array on both sides (RGBA output depends on the slice shape: no merging)
+        // a run of slices that is one contiguous block array on both sides.  RGBA output depends on the slice shape, but
+        // slices of the same width that follow each other are one taller image (a batch of equally sized textures)
         uint64_t n = slices[i].nblocks;
         uint32_t j = i + 1;
-        if (target != B2BU_RGBA)
-            while (j < num_slices && slices[j].in_ofs == slices[i].in_ofs + n * 16 && slices[j].out_ofs == slices[i].out_ofs + n * ob) n += slices[j++].nblocks;
+        while (j < num_slices && slices[j].in_ofs == slices[i].in_ofs + n * 16 && slices[j].out_ofs == slices[i].out_ofs + n * ob &&
+               (target != B2BU_RGBA || slices[j].blocks_per_row == slices[i].blocks_per_row))
+            n += slices[j++].nblocks;
         if (n) {
             uint64_t skip = 0;
             if (target == B2BU_ETC1 && (slices[i].out_ofs & 15)) {

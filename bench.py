@@ -403,7 +403,7 @@ def bench_c4_etc1s(L, b, nb=1024, slices=64, n_cb=4096, reps=2):
 def bench_c5_mixed_batch(L, b, torch, dist, rank, world, payload, total_images, status, sh):
     """configs[4]: a batch of mixed UASTC / ETC1S 2048x2048 textures sharded by image over the ranks (image i -> rank i mod world,
     basisu_rs_b200.shard.plan_shards), no collective on the data path.  UASTC images go to RGBA and BC7 through the device-resident
-    entry point (one launch per image); ETC1S images go to RGBA (the reference has no ETC1S -> BC7) through b2bu_etc1s_transcode_slices,
+    slice-table entry point (the rank's images in one launch); ETC1S images go to RGBA (the reference has no ETC1S -> BC7) through b2bu_etc1s_transcode_slices,
     whose device phases (K2 + K3) are timed by the library.  BASELINE names 4096 images; the default measures `total_images` of them."""
     import etc1s_common as ec
     from etc1s_synth import encode, make_codebooks, make_indices
@@ -415,26 +415,53 @@ def bench_c5_mixed_batch(L, b, torch, dist, rank, world, payload, total_images, 
     es = [i for i in mine if i % 2 == 1]
     res = {"workload": "%d textures of 2048x2048 (even = UASTC, odd = ETC1S), image i on rank i mod %d" % (total_images, world),
            "images_this_rank": len(mine)}
-    # ---- UASTC share: distinct device buffers per image, seeded by the image index ----
+    # ---- UASTC share: the rank's images back to back in one device buffer (seeded by the image index), transcoded by ONE call of
+    # b2bu_uastc_transcode_slices_dev per target: equally sized images are contiguous on both sides and merge into one launch.
+    # The per-image launch loop is timed beside it (2048x2048 is 1771 blocks per SM: a launch of its own never leaves the
+    # pipeline's start-up phase).
     t_rgba = t_bc7 = 0.0
+    per_image = {}
     if ua:
-        d_in = [torch.from_numpy(make_payload(payload, nblk, seed=1000 + i).reshape(-1)).cuda() for i in ua]
-        o_rgba = [torch.empty(nblk * 64, dtype=torch.uint8, device="cuda") for _ in range(min(len(ua), 8))]
-        o_bc7 = [torch.empty(nblk * 16, dtype=torch.uint8, device="cuda") for _ in range(min(len(ua), 8))]
-        for tgt, outs, ob in ((0, o_rgba, 64), (2, o_bc7, 16)):
-            for rep in range(2):
-                a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                for k in range(len(ua)):
-                    assert L.b2bu_uastc_transcode_dev(tgt, d_in[k].data_ptr(), nblk * 16, nb, outs[k % len(outs)].data_ptr(), nblk * ob,
-                                                      status.data_ptr(), sh) == 0
-                c.record()
-                torch.cuda.synchronize()
-            if tgt == 0:
-                t_rgba = a.elapsed_time(c) * 1e-3
-            else:
-                t_bc7 = a.elapsed_time(c) * 1e-3
-        del d_in, o_rgba, o_bc7
+        allb = np.concatenate([make_payload(payload, nblk, seed=1000 + i) for i in ua])
+        d_all = torch.from_numpy(allb.reshape(-1)).cuda()
+        nimg = len(ua)
+        for tgt, ob in ((0, 64), (2, 16)):
+            d_out = torch.empty(nimg * nblk * ob, dtype=torch.uint8, device="cuda")
+            sl = (b.SliceDev * nimg)()
+            for k in range(nimg):
+                sl[k] = b.SliceDev(k * nblk * 16, k * nblk * ob, nblk, nb, 0)
+            for mode in ("batched", "per_image"):
+                for rep in range(2):
+                    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    if mode == "batched":
+                        assert L.b2bu_uastc_transcode_slices_dev(tgt, d_all.data_ptr(), d_out.data_ptr(), sl, nimg, status.data_ptr(), sh) == 0
+                    else:
+                        for k in range(nimg):
+                            assert L.b2bu_uastc_transcode_dev(tgt, d_all.data_ptr() + k * nblk * 16, nblk * 16, nb, d_out.data_ptr() + k * nblk * ob,
+                                                              nblk * ob, status.data_ptr(), sh) == 0
+                    c.record()
+                    torch.cuda.synchronize()
+                t = a.elapsed_time(c) * 1e-3
+                if mode == "batched":
+                    if tgt == 0:
+                        t_rgba = t
+                    else:
+                        t_bc7 = t
+                    if rank == 0:                        # parity of the batched result: first and last image against the oracle
+                        orc_u = load_oracle()
+                        got = d_out.cpu().numpy()
+                        okp = True
+                        for k in (0, nimg - 1):
+                            want = np.zeros(nblk * ob, dtype=np.uint8)
+                            orc_u.orc_uastc_transcode_slice(tgt, allb[k * nblk:].ctypes.data, nblk * 16, nb, want.ctypes.data, os.cpu_count() or 1, None)
+                            okp = okp and bool((got[k * nblk * ob:(k + 1) * nblk * ob] == want).all())
+                        res["uastc_%s_parity_vs_oracle" % ("rgba" if tgt == 0 else "bc7")] = okp
+                else:
+                    per_image["rgba" if tgt == 0 else "bc7"] = nimg * nblk * 16 / t / 1e9
+            del d_out
+        del d_all
+        res["uastc_one_launch_per_image_gtexel_s_this_rank"] = per_image
     # ---- ETC1S share: one encoded 512x512-block slice per image (same codebooks), all slices of the rank in one call ----
     t_etc = 0.0
     if es:

@@ -107,9 +107,10 @@ int b2bu_uastc_transcode_dev(int target, const void* d_blocks, size_t nbytes, si
  * (basis.rs:145-260 loop over the slice descriptors and call Decoder::transcode once per slice).  in_ofs /
  * out_ofs are byte offsets from d_blocks / d_out (multiples of 16; out_ofs of B2BU_ETC1: of 8, so that
  * slices with odd block counts can be packed back to back); blocks_per_row is only used by
- * B2BU_RGBA.  For the other targets, slices that follow each other without a gap in both buffers are
- * merged into ONE kernel launch: a full mip chain is a single launch instead of 14.  In d_status, block
- * indices count through the slices in array order. */
+ * B2BU_RGBA.  Slices that follow each other without a gap in both buffers are merged into ONE kernel
+ * launch (B2BU_RGBA: if they also have the same blocks_per_row, i.e. form one taller image): a full mip
+ * chain is a single launch instead of 14, a batch of equally sized textures is one launch.  In d_status,
+ * block indices count through the slices in array order. */
 typedef struct b2bu_slice_dev {
     uint64_t in_ofs, out_ofs, nblocks;
     uint32_t blocks_per_row, reserved;

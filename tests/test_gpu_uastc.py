@@ -271,7 +271,8 @@ def test_slices_dev_runs_a_mip_chain_in_one_launch(gpu_lib, oracle):
         before = L.b2bu_launch_count()
         assert L.b2bu_uastc_transcode_slices_dev(t, d_in.data_ptr(), d_out.data_ptr(), sl, len(levels), status.data_ptr(), stream) == 0
         launches = L.b2bu_launch_count() - before
-        assert launches == (len(levels) if t == 0 else 1)         # RGBA depends on the slice shape; the others merge
+        # RGBA output depends on the slice width: only neighbours of equal width merge (the 1x1 tail levels); the others always do
+        assert launches == (1 + sum(levels[k] != levels[k - 1] for k in range(1, len(levels))) if t == 0 else 1)
         assert L.b2bu_status_read_dev(status.data_ptr(), stream, None) == 0
         got = d_out.cpu().numpy()
         pos = 0
@@ -365,3 +366,30 @@ def test_read_to_pipelined_upload_of_a_multi_piece_file(gpu_lib, oracle):
     with pytest.raises(gpu_lib.BasisuError) as ei:
         gpu_lib.read_to_uastc(bytes(g))
     assert str(ei.value) == "Data CRC16 failed"
+
+
+def test_slices_dev_batch_of_equal_textures_is_one_launch(gpu_lib, oracle):
+    """BASELINE configs[4] in miniature: equally sized textures back to back in one buffer are one launch for every target,
+    RGBA included (same blocks_per_row: the batch is one taller image)."""
+    import torch
+    L = gpu_lib.lib()
+    nb, nimg = 96, 5
+    blocks = [random_blocks(nb * nb, seed=700 + k) for k in range(nimg)]
+    d_in = torch.from_numpy(np.concatenate(blocks).reshape(-1).copy()).cuda()
+    status = torch.zeros(1, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    for t in range(5):
+        ob = OUT_BYTES[t]
+        sl = (gpu_lib.SliceDev * nimg)()
+        for k in range(nimg):
+            sl[k] = gpu_lib.SliceDev(k * nb * nb * 16, k * nb * nb * ob, nb * nb, nb, 0)
+        d_out = torch.zeros(nimg * nb * nb * ob, dtype=torch.uint8, device="cuda")
+        assert L.b2bu_status_reset_dev(status.data_ptr(), stream) == 0
+        before = L.b2bu_launch_count()
+        assert L.b2bu_uastc_transcode_slices_dev(t, d_in.data_ptr(), d_out.data_ptr(), sl, nimg, status.data_ptr(), stream) == 0
+        assert L.b2bu_launch_count() - before == 1
+        assert L.b2bu_status_read_dev(status.data_ptr(), stream, None) == 0
+        got = d_out.cpu().numpy()
+        for k in range(nimg):
+            _, _, want = oracle_transcode(oracle, t, blocks[k], nb)
+            assert (got[k * nb * nb * ob:(k + 1) * nb * nb * ob] == want).all(), (t, k)
