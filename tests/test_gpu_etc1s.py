@@ -202,3 +202,28 @@ def test_config4_shape_slices_property(gpu_lib, oracle):
     assert dec.decode_to_rgba(nbx, nby, slice_bytes(enc, 1)) == want
     dec.close()
     orc.orc_etc1s_close(h)
+
+
+@pytest.mark.parametrize("nbx,nby,ns,ncb", [(64, 33, 300, 700), (40, 40, 1300, 256)])
+def test_many_slices_pack_several_pipelines_per_cta(gpu_lib, oracle, nbx, nby, ns, ncb):
+    """More slices than SMs: the launch packs up to 8 two-warp pipelines into a CTA (shared tables, the narrow table set) and
+    runs several waves.  Every slice must still decode exactly, run after run."""
+    orc = bind(oracle)
+    _, _, ei, si, enc = make_case(orc, nbx, nby, 10, ncb, seed=ns)
+    uniq = len(enc["slice_ofs"])
+    e, h = oracle_open(orc, enc, ncb, ncb)
+    want = [oracle_etc1(orc, h, nbx, nby, slice_bytes(enc, k))[1] for k in range(uniq)]
+    dec = gpu_lib.Etc1sDecoder(ncb, ncb, enc["endpoints"], enc["selectors"], enc["tables"])
+    L = gpu_lib.lib()
+    ofs = (ctypes.c_uint64 * ns)(*[enc["slice_ofs"][k % uniq] for k in range(ns)])
+    ln = (ctypes.c_uint64 * ns)(*[enc["slice_len"][k % uniq] for k in range(ns)])
+    per = nbx * nby * 8
+    out = np.zeros(ns * per, dtype=np.uint8)
+    for rep in range(3):
+        out[:] = 0
+        assert L.b2bu_etc1s_transcode_slices(dec._h, gpu_lib.ETC1, nbx, nby, enc["slice_data"], len(enc["slice_data"]), ofs, ln, ns,
+                                             out.ctypes.data, out.size) == 0
+        for k in range(ns):
+            assert out[k * per:(k + 1) * per].tobytes() == want[k % uniq], (rep, k)
+    dec.close()
+    orc.orc_etc1s_close(h)
