@@ -44,10 +44,11 @@ __host__ __device__ inline uint64_t etc1s_row_state_bytes(uint32_t nbx)
 
 // Launch shape of K2.  pipes: slice pipelines (one tokenizer warp + one resolver warp each) per CTA -- the slices are spread
 // over the SMs first and packed only when there are more slices than SMs; row_cap: widest slice whose previous-row state
-// fits in shared memory (wider slices keep it in the scratch area); big_tables: a CTA that decodes a single slice has room
-// for the wide first-level tables (the host keeps two sets, see etc1s_host.cu).
-struct Etc1sDecodePlan { int pipes; uint32_t row_cap; int big_tables; };
-Etc1sDecodePlan plan_etc1s_decode(uint32_t num_slices, uint32_t max_nbx, int sm_count, uint32_t l1_words_small, uint32_t l1_words_big);
+// fits in shared memory (wider slices keep it in the scratch area); table_set: the host keeps kEtc1sTableSets sets of
+// first-level tables of growing size (see etc1s_host.cu) and the launch takes the largest one that fits beside the pipelines.
+constexpr int kEtc1sTableSets = 3;
+struct Etc1sDecodePlan { int pipes; uint32_t row_cap; int table_set; };
+Etc1sDecodePlan plan_etc1s_decode(uint32_t num_slices, uint32_t max_nbx, int sm_count, const uint32_t l1_words[kEtc1sTableSets]);
 cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, const Etc1sDecodePlan& plan, cudaStream_t stream);
 cudaError_t launch_etc1s_gather_etc1(const uint32_t* idx, uint64_t nblocks, const uint32_t* endpoints, const uint32_t* sel_etc1, void* out,
                                      int sm_count, cudaStream_t stream);

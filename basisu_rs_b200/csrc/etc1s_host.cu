@@ -19,10 +19,11 @@ namespace b2bu {
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
 
-// Shared memory given to the four first-level Huffman tables of K2 (the rest holds the per-slice pipelines).  Two sets are
-// kept per file: a wide one for launches with one slice per SM (a lone pipeline leaves ~210 KB free) and a narrow one for
-// batches that pack several slice pipelines into a CTA.
-constexpr size_t kL1BudgetBytes[2] = {96 * 1024, 208 * 1024};
+// Shared memory given to the four first-level Huffman tables of K2 (the rest holds the per-slice pipelines).  Three sets
+// are kept per file: a wide one for launches with one slice per SM (a lone pipeline leaves ~210 KB free), a medium one that
+// still fits beside 8 pipelines of ordinary width (codes that miss the first level cost a global-memory lookup and a redone
+// pair: 592 slices of 512x512 blocks went from 59 to 34 ms with it), and a narrow one for very wide slices.
+constexpr size_t kL1BudgetBytes[kEtc1sTableSets] = {96 * 1024, 160 * 1024, 208 * 1024};
 
 // ---- bit cursor: LSB first, bytes past the end read as zero (src/bitreader.rs:27-60) ----------
 struct BitCursor {
@@ -184,9 +185,9 @@ struct b2bu_etc1s {
     uint32_t* d_endpoints = nullptr;     // inten | r5 << 8 | g5 << 16 | b5 << 24
     uint32_t* d_sel_plain = nullptr;     // 4 rows, 2 bits per x          (etc.rs:343-361)
     uint32_t* d_sel_etc1 = nullptr;      // ETC1 bit planes               (etc.rs:363-393)
-    // [0] narrow / [1] wide set of the four first-level tables, back to back
-    uint32_t* d_l1[2] = {nullptr, nullptr};
-    uint32_t l1_bits[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, l1_ofs[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    // narrow / medium / wide set of the four first-level tables, each set back to back
+    uint32_t* d_l1[kEtc1sTableSets] = {};
+    uint32_t l1_bits[kEtc1sTableSets][4] = {}, l1_ofs[kEtc1sTableSets][5] = {};
     int last_set = 0;                    // table set used by the last call
     uint32_t* d_flat[4] = {nullptr, nullptr, nullptr, nullptr};
     // per-call scratch (grow only)
@@ -275,8 +276,10 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
     P.num_slices = (uint32_t)ns;
     P.out_idx = static_cast<uint32_t*>(h->d_idx);
     P.scratch = static_cast<uint8_t*>(h->d_scratch);
-    const Etc1sDecodePlan dplan = plan_etc1s_decode((uint32_t)ns, max_nbx, c->sm_count, h->l1_ofs[0][4], h->l1_ofs[1][4]);
-    const int set = dplan.big_tables ? 1 : 0;
+    uint32_t l1_words[kEtc1sTableSets];
+    for (int k = 0; k < kEtc1sTableSets; k++) l1_words[k] = h->l1_ofs[k][4];
+    const Etc1sDecodePlan dplan = plan_etc1s_decode((uint32_t)ns, max_nbx, c->sm_count, l1_words);
+    const int set = dplan.table_set;
     h->last_set = set;
     P.l1 = h->d_l1[set];
     for (int t = 0; t < 4; t++) { P.flat[t] = h->d_flat[t]; P.max_len[t] = h->max_len[t]; P.l1_bits[t] = h->l1_bits[set][t]; P.l1_ofs[t] = h->l1_ofs[set][t]; }
@@ -382,9 +385,9 @@ static int etc1s_open_impl(uint32_t endpoint_count, uint32_t selector_count, con
         for (int t = 0; t < 4; t++) if ((st = read_huffman_table(bc, models[t]))) return st;
         h->hist_size = bc.read(13);
     }
-    std::vector<uint32_t> l1[2];
+    std::vector<uint32_t> l1[kEtc1sTableSets];
     const uint32_t run_sym[4] = {256u, 0xFFFFFFFFu, (h->hist_size + selector_count) & 0xFFFFu, 0xFFFFFFFFu};   // mod.rs:220-222
-    for (int set = 0; set < 2; set++) {
+    for (int set = 0; set < kEtc1sTableSets; set++) {
         unsigned bits[4];
         choose_l1_bits(models, kL1BudgetBytes[set], bits);
         for (int t = 0; t < 4; t++) {
@@ -397,7 +400,7 @@ static int etc1s_open_impl(uint32_t endpoint_count, uint32_t selector_count, con
 
     CK(cudaSetDevice(h->device));
     if ((st = upload(&h->d_endpoints, endpoints)) || (st = upload(&h->d_sel_plain, sel_plain)) || (st = upload(&h->d_sel_etc1, sel_etc1)) ||
-        (st = upload(&h->d_l1[0], l1[0])) || (st = upload(&h->d_l1[1], l1[1]))) return st;
+        (st = upload(&h->d_l1[0], l1[0])) || (st = upload(&h->d_l1[1], l1[1])) || (st = upload(&h->d_l1[2], l1[2]))) return st;
     for (int t = 0; t < 4; t++) if ((st = upload(&h->d_flat[t], models[t].flat))) return st;
     *out = h.release();
     return B2BU_OK;
@@ -457,7 +460,7 @@ void b2bu_etc1s_close(b2bu_etc1s* h)
     if (!h) return;
     cudaSetDevice(h->device);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    cudaFree(h->d_endpoints); cudaFree(h->d_sel_plain); cudaFree(h->d_sel_etc1); cudaFree(h->d_l1[0]); cudaFree(h->d_l1[1]);
+    cudaFree(h->d_endpoints); cudaFree(h->d_sel_plain); cudaFree(h->d_sel_etc1); for (int k = 0; k < kEtc1sTableSets; k++) cudaFree(h->d_l1[k]);
     for (int t = 0; t < 4; t++) cudaFree(h->d_flat[t]);
     cudaFree(h->d_data); cudaFree(h->d_idx); cudaFree(h->d_out); cudaFree(h->d_scratch); cudaFree(h->d_jobs); cudaFree(h->d_status);
     delete h;

@@ -752,19 +752,22 @@ static size_t etc1s_decode_smem_bytes(uint32_t l1_words, int pipes, uint32_t row
 
 constexpr size_t kK2SmemLimit = 224 * 1024;
 
-Etc1sDecodePlan plan_etc1s_decode(uint32_t num_slices, uint32_t max_nbx, int sm_count, uint32_t l1_words_small, uint32_t l1_words_big)
+Etc1sDecodePlan plan_etc1s_decode(uint32_t num_slices, uint32_t max_nbx, int sm_count, const uint32_t l1_words[kEtc1sTableSets])
 {
     Etc1sDecodePlan plan;
     int pipes = (int)((num_slices + (uint32_t)sm_count - 1u) / (uint32_t)(sm_count > 0 ? sm_count : 1));
     if (pipes < 1) pipes = 1;
     if (pipes > 8) pipes = 8;                                 // 512 threads: the tokenizer wants more than 64 registers
     uint32_t row_cap = (max_nbx + 31u) & ~31u;
-    plan.big_tables = pipes == 1 && etc1s_decode_smem_bytes(l1_words_big, 1, row_cap) <= kK2SmemLimit;
-    const uint32_t l1_words = plan.big_tables ? l1_words_big : l1_words_small;
-    if (etc1s_decode_smem_bytes(l1_words, 1, row_cap) > kK2SmemLimit) row_cap = 0;            // very wide slices: row state in global scratch
-    while (pipes > 1 && etc1s_decode_smem_bytes(l1_words, pipes, row_cap) > kK2SmemLimit) pipes--;
+    // the largest table set that fits beside `pipes` pipelines with their row state in shared memory; failing that, the
+    // smallest set with the row state in global scratch and as many pipelines as fit
+    int set = kEtc1sTableSets - 1;
+    while (set > 0 && etc1s_decode_smem_bytes(l1_words[set], pipes, row_cap) > kK2SmemLimit) set--;
+    if (etc1s_decode_smem_bytes(l1_words[set], 1, row_cap) > kK2SmemLimit) row_cap = 0;       // very wide slices
+    while (pipes > 1 && etc1s_decode_smem_bytes(l1_words[set], pipes, row_cap) > kK2SmemLimit) pipes--;
     plan.pipes = pipes;
     plan.row_cap = row_cap;
+    plan.table_set = set;
     return plan;
 }
 
