@@ -157,6 +157,13 @@ __device__ unsigned long long g_trace[160][64];
 #ifndef B2BU_SORT_UNIFORM
 #define B2BU_SORT_UNIFORM 0     // measured: ASTC shuffled 55 -> 62 us, coherent 64 -> 62 us; off
 #endif
+// With B2BU_SUBLOAD a tile is loaded as several bulk copies with a barrier each, so that the sorter classifies the first
+// part while the rest is still arriving (the load of a 64 KiB tile takes ~3000 cycles when all SMs load at once).  Measured:
+// ASTC 56 -> 58 us -- like every other attempt to overlap the stages more, it loses: the SM is short of issue slots, not of
+// overlap.  Off.
+#ifndef B2BU_SUBLOAD
+#define B2BU_SUBLOAD 0
+#endif
 #ifndef B2BU_STATIC_BC7
 #define B2BU_STATIC_BC7 0
 #endif
@@ -189,6 +196,9 @@ template <int TARGET> struct PipeCfg {
     static constexpr int WORK_WARPS = B2BU_WORK_WARPS;
     static constexpr int THREADS = 32 * (1 + SORT_WARPS + WORK_WARPS);
     static constexpr int PERS = (TILE + SORT_THREADS - 1) / SORT_THREADS;     // blocks per sorter thread
+    static constexpr int SUB = !B2BU_SUBLOAD ? TILE : (TILE % 1024 == 0 ? 1024 : TILE % 512 == 0 ? 512 : TILE);   // blocks per bulk load
+    static constexpr int NSUB = TILE / SUB;
+    static_assert(SUB % SORT_THREADS == 0 || NSUB == 1, "a sub-load must be whole sorter passes");
     static constexpr int MAXORD = TILE + kBins * 32;
     static constexpr int MAXITEMS = MAXORD / 32;
     static constexpr size_t OFF_IN = (TableBytes<TARGET>::value + 127) / 128 * 128;   // two slots
@@ -201,7 +211,7 @@ template <int TARGET> struct PipeCfg {
     static constexpr size_t OFF_BASE = OFF_WCNT + (size_t)SORT_WARPS * 32 * 4;
     static constexpr size_t OFF_CTL = OFF_BASE + (size_t)SORT_WARPS * 32 * 4;
     static constexpr size_t OFF_BAR = (OFF_CTL + NS * 4 * 4 + 7) / 8 * 8;
-    static constexpr size_t SMEM = OFF_BAR + 3 * NS * 8;
+    static constexpr size_t SMEM = OFF_BAR + (NSUB + 2) * NS * 8;
     static_assert(SMEM <= 227 * 1024, "tile configuration does not fit shared memory");
     static_assert(THREADS <= 1024, "too many warps");
 };
@@ -230,7 +240,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
     uint32_t* wbase = reinterpret_cast<uint32_t*>(smem + C::OFF_BASE);        // [SORT_WARPS][32]
     uint32_t* ctl = reinterpret_cast<uint32_t*>(smem + C::OFF_CTL);           // [2][4]: next item, number of items
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);          // full[2], sorted[2], done[2]
-    uint64_t* bar_full = bars, *bar_sorted = bars + C::NS, *bar_done = bars + 2 * C::NS;
+    uint64_t* bar_full = bars, *bar_sorted = bars + C::NS * C::NSUB, *bar_done = bar_sorted + C::NS;        // full[NS][NSUB]
 
     // role order by hardware warp id: B2BU_SORT_FIRST = 1 puts the sorter warps at the low ids
 #ifndef B2BU_SORT_FIRST
@@ -265,7 +275,8 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
     auto tile_blocks = [&](uint32_t k) -> uint32_t { return tile_start(k + 1) - tile_start(k); };
 
     if (tid == 0) {
-        for (int i = 0; i < C::NS; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_sorted[i], 1); mbar_init(&bar_done[i], C::WORK_WARPS); }
+        for (int i = 0; i < C::NS * C::NSUB; i++) mbar_init(&bar_full[i], 1);
+        for (int i = 0; i < C::NS; i++) { mbar_init(&bar_sorted[i], 1); mbar_init(&bar_done[i], C::WORK_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     load_tables(&T, TableBytes<TARGET>::value);  // ends with __syncthreads()
@@ -311,9 +322,14 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
                 store_tile(k - C::NS);
                 tma_store_wait_read();
             }
-            const uint32_t bytes = tile_blocks(k) * 16u;
-            mbar_expect_tx(&bar_full[s], bytes);
-            tma_load_1d(in_s + s * C::TILE, in + r0 + tile_start(k), bytes, &bar_full[s]);
+            const uint32_t ntk = tile_blocks(k);
+#pragma unroll
+            for (int q = 0; q < C::NSUB; q++) {                // every part's barrier completes once per tile, empty parts too
+                const uint32_t lo = (uint32_t)(q * C::SUB), hi = ntk < lo + (uint32_t)C::SUB ? ntk : lo + (uint32_t)C::SUB;
+                const uint32_t bytes = hi > lo ? (hi - lo) * 16u : 0u;
+                mbar_expect_tx(&bar_full[s * C::NSUB + q], bytes);
+                if (bytes) tma_load_1d(in_s + s * C::TILE + lo, in + r0 + tile_start(k) + lo, bytes, &bar_full[s * C::NSUB + q]);
+            }
             do { if (k < 6) TRACE(k * 6 + 0); } while (0);
         }
         for (uint32_t k = ntiles >= (uint32_t)C::NS ? ntiles - C::NS : 0; k < ntiles; k++) {
@@ -338,7 +354,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
             const uint4* tin = in_s + s * C::TILE;
             mycnt[lane] = 0;
             __syncwarp();
-            mbar_wait(&bar_full[s], u & 1u);
+            mbar_wait(&bar_full[s * C::NSUB], u & 1u);
             if (st == 0) do { if (k < 6) TRACE(k * 6 + 1); } while (0);
             // A: classify, rank inside (warp, mode).  Shared-memory latency is hundreds of cycles while the workers
             // keep the LSU busy, so every step is a branch-free pass over all of the thread's blocks (PERS loads /
@@ -355,6 +371,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
             for (int j = 0; j < C::PERS; j++) {
                 // blocks past the end of a short tile read stale slot contents (always inside the slot); they are discarded below
                 mr[j] = 31u;
+                if (j > 0 && (j * C::SORT_THREADS) % C::SUB == 0 && j < jmax) mbar_wait(&bar_full[s * C::NSUB + (j * C::SORT_THREADS) / C::SUB], u & 1u);
                 if (j < jmax) mr[j] = tin[bst + j * C::SORT_THREADS].x & 127u;
             }
 #pragma unroll
@@ -457,7 +474,8 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
 #ifdef B2BU_TRACE
         if (lane == 0) { if (warp == 0) { TRACE_ADD(61, clock64() - tw0); do { if (k < 6) TRACE(k * 6 + 3); } while (0); } if (warp == C::WORK_WARPS - 1) TRACE_ADD(62, clock64() - tw0); }
 #endif
-        mbar_wait(&bar_full[s], u & 1u);          // completed long ago: observes the bulk-copied bytes directly
+#pragma unroll
+        for (int q = 0; q < C::NSUB; q++) mbar_wait(&bar_full[s * C::NSUB + q], u & 1u);   // completed long ago: observes the bulk-copied bytes directly
         const uint32_t nitems = ctl[s * 4 + 1];
         const uint32_t bt = bintab[s * 32 + lane];
         // Items are pulled in bin order from a shared counter.  Besides balancing uneven items this keeps every worker of
