@@ -1,5 +1,7 @@
 // Tuning aid: latency of a dependent chain through shared-memory loads for one warp, with the load (a) always executed,
-// (b) predicated off, (c) absent -- does a predicated-off LDS still cost its consumer the load latency?
+// (b) predicated off, (c) absent -- does a predicated-off LDS still cost its consumer the load latency?  (It does.)
+// build here, run on the GPU box:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/bin/probe_pred_lds tools/probe_pred_lds.cu
+//                                  gpurun -- ./tools/bin/probe_pred_lds
 #include <cstdio>
 #include <cuda_runtime.h>
 __global__ void probe(unsigned* out, int iters, int mode)
