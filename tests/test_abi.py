@@ -54,6 +54,24 @@ def test_host_only_entry_points_work_without_gpu():
     assert L.b2bu_read_to(b.BC7, f, 40, None, None, 0, ctypes.byref(cnt), None, 0, ctypes.byref(need)) == 10
 
 
+def test_sizing_call_of_a_large_file_leaves_the_data_crc_to_the_decoding_call():
+    """Files of 256 KiB and more are CRC-checked by the GPU inside the decoding call; the host-only sizing call (out == NULL) must
+    not spend a single-core CRC pass on them (and so cannot report a data CRC error), while small files keep the host check."""
+    import basisu_rs_b200 as b
+    from basis_writer import uastc_file
+    L = b.lib()
+    cnt, need = ctypes.c_uint32(0), ctypes.c_uint64(0)
+    big = np.zeros((160 * 128, 16), dtype=np.uint8).tobytes()          # 320 KiB of (valid mode 11) zero blocks
+    g = uastc_file(big, 160, 128, corrupt="data")
+    assert len(g) >= 256 * 1024
+    assert L.b2bu_read_to(b.BC7, g, len(g), None, None, 0, ctypes.byref(cnt), None, 0, ctypes.byref(need)) == 0
+    assert (cnt.value, need.value) == (1, 160 * 128 * 16)
+    # read_to_uastc (a plain copy, never on the device) still verifies on the host, sizing call aside
+    out = (ctypes.c_uint8 * need.value)()
+    imgs = (b._CImage * 1)()
+    assert L.b2bu_read_to(b.UASTC, g, len(g), None, imgs, 1, ctypes.byref(cnt), out, need.value, ctypes.byref(need)) == 12
+
+
 def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
     import basisu_rs_b200 as b
     monkeypatch.setattr(b, "_LIB", None)
