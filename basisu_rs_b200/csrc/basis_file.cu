@@ -7,6 +7,7 @@
 // launch and a sync cost more than a few KB of table lookups).
 #include <algorithm>
 #include <cstring>
+#include <new>
 #include <vector>
 
 #include "../../include/b2bu.h"
@@ -94,8 +95,24 @@ static int finish_device_crc(DeviceCtx* c, cudaStream_t s, uint64_t crc_len, uin
     return body_status;
 }
 
+static int read_to_impl(int target, const uint8_t* buf, size_t len, b2bu_header* header, b2bu_image* images, uint32_t max_images,
+                        uint32_t* num_images, uint8_t* out, uint64_t out_cap, uint64_t* out_needed);
+
 int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header, b2bu_image* images, uint32_t max_images,
                  uint32_t* num_images, uint8_t* out, uint64_t out_cap, uint64_t* out_needed)
+{
+    // exception barrier: the body allocates (slice table, plans); nothing may unwind through the C ABI
+    try {
+        return read_to_impl(target, buf, len, header, images, max_images, num_images, out, out_cap, out_needed);
+    } catch (const std::bad_alloc&) {
+        return B2BU_ERR_NOMEM;
+    } catch (...) {
+        return B2BU_ERR_ARGUMENT;
+    }
+}
+
+static int read_to_impl(int target, const uint8_t* buf, size_t len, b2bu_header* header, b2bu_image* images, uint32_t max_images,
+                        uint32_t* num_images, uint8_t* out, uint64_t out_cap, uint64_t* out_needed)
 {
     if (num_images) *num_images = 0;
     if (out_needed) *out_needed = 0;
@@ -128,6 +145,7 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
     }
     // whole-file upload + CRC in one piece (ETC1S files, and UASTC files whose slices cannot be transcoded in place)
     bool uploaded = false;
+    bool hard_fail = false;                        // a CUDA / launch failure of the pipelined path: the partial CRC means nothing
     auto upload_all = [&]() -> int {
         if (!gpu_crc || uploaded) return B2BU_OK;
         uploaded = true;
@@ -139,7 +157,10 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
     // everything below is the body after the CRC check; with the device CRC in flight its status is held back until the CRC is known
     auto body = [&]() -> int {
     // basis.rs:343-362 read_slice_descs
-    std::vector<SliceDesc> descs(h.total_slices);
+    // total_slices is a 24-bit field of an unverified header: size the table by what the file can hold (the loop below
+    // fails at the first descriptor that does not fit, before it could index past this)
+    const uint64_t desc_fit = (uint64_t)h.slice_desc_file_ofs <= len ? (len - h.slice_desc_file_ofs) / 23 : 0;
+    std::vector<SliceDesc> descs((size_t)std::min<uint64_t>(h.total_slices, desc_fit + 1));
     for (uint32_t i = 0; i < h.total_slices; i++) {
         const size_t start = (size_t)h.slice_desc_file_ofs + (size_t)i * 23;
         if (start > len) return B2BU_ERR_RANGE;                                     // reference: slice index panic
@@ -226,13 +247,20 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
         std::vector<uint64_t> done_blocks(nimg, 0), base_blocks(nimg, 0);
         for (uint32_t i = 1; i < nimg; i++) base_blocks[i] = base_blocks[i - 1] + descs[i - 1].file_size / 16;
         std::vector<cudaEvent_t> evs;
-        auto new_event = [&](cudaStream_t s) -> cudaEvent_t { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); cudaEventRecord(e, s); evs.push_back(e); return e; };
-        cudaStreamWaitEvent(sK, new_event(s0), 0);                                  // the status / CRC words are reset on s0
         int rc = B2BU_OK;
+        // order `waiter` behind everything queued on `src` so far; a failed event would silently drop the ordering
+        auto chain = [&](cudaStream_t waiter, cudaStream_t src) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { rc = B2BU_ERR_CUDA; return; }
+            evs.push_back(e);
+            if (cudaEventRecord(e, src) != cudaSuccess || cudaStreamWaitEvent(waiter, e, 0) != cudaSuccess) rc = B2BU_ERR_CUDA;
+        };
+        chain(sK, s0);                                                              // the status / CRC words are reset on s0
         for (uint64_t pos = 0; pos < len && rc == B2BU_OK;) {
             const uint64_t n = std::min<uint64_t>(kFilePieceBytes, len - pos);
             if (cudaMemcpyAsync(d_file + pos, buf + pos, n, cudaMemcpyHostToDevice, sH) != cudaSuccess) { rc = B2BU_ERR_CUDA; break; }
-            cudaStreamWaitEvent(sK, new_event(sH), 0);
+            chain(sK, sH);
+            if (rc != B2BU_OK) break;
             const uint64_t up = pos + n;                                            // file bytes [0, up) are on the device
             if (up > 77) {
                 const uint64_t from = std::max<uint64_t>(pos, 77);
@@ -262,7 +290,8 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
                     a = b;
                 }
                 if (rc != B2BU_OK) break;
-                cudaStreamWaitEvent(sD, new_event(sK), 0);
+                chain(sD, sK);
+                if (rc != B2BU_OK) break;
                 for (size_t k = 0; k < sl.size(); k++) {
                     if (cudaMemcpyAsync(out + sl[k].out_ofs, d_out + sl[k].out_ofs, sl[k].nblocks * ob, cudaMemcpyDeviceToHost, sD) != cudaSuccess) { rc = B2BU_ERR_CUDA; break; }
                     done_blocks[which[k]] += sl[k].nblocks;
@@ -271,13 +300,12 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
             pos = up;
         }
         // everything funnels back into s0, where the caller waits for the CRC word
-        cudaStreamWaitEvent(s0, new_event(sK), 0);
-        cudaStreamWaitEvent(s0, new_event(sD), 0);
+        { const int keep = rc; rc = B2BU_OK; chain(s0, sK); chain(s0, sD); if (keep != B2BU_OK) rc = keep; }
         if (rc == B2BU_OK && cudaMemcpyAsync(c->h_err, c->d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s0) != cudaSuccess) rc = B2BU_ERR_CUDA;
         const cudaError_t es = cudaStreamSynchronize(s0);
         for (cudaEvent_t e : evs) cudaEventDestroy(e);
-        if (rc != B2BU_OK) return rc == B2BU_ERR_CUDA ? cuda_fail(cudaGetLastError(), "pipelined file path") : rc;
-        if (es != cudaSuccess) return cuda_fail(es, "cudaStreamSynchronize");
+        if (rc != B2BU_OK) { hard_fail = true; return rc == B2BU_ERR_CUDA ? cuda_fail(cudaGetLastError(), "pipelined file path") : rc; }
+        if (es != cudaSuccess) { hard_fail = true; return cuda_fail(es, "cudaStreamSynchronize"); }
         return decode_status_word(*c->h_err, nullptr);
     }
     if ((st2 = upload_all())) return st2;
@@ -317,6 +345,14 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
     return decode_status_word(*c->h_err, nullptr);
     };
     st = body();
+    if (big && out == nullptr && !plain_copy && st != B2BU_OK) {
+        // Sizing call of a large file: the data CRC has not been looked at, and the reference reports it before any error of
+        // the body (basis.rs:9-13).  The verdict -- CRC first -- belongs to the transcoding call (see b2bu.h).
+        if (num_images) *num_images = 0;
+        if (out_needed) *out_needed = 0;
+        return B2BU_OK;
+    }
+    if (gpu_crc && hard_fail) return st;                 // the real failure, not a comparison against a partial CRC
     if (gpu_crc) {
         const int su = upload_all();                     // an early return of the body must not skip the CRC: its verdict comes first
         if (su) return su;

@@ -171,6 +171,7 @@ const char* b2bu_error_string(int status)
     case B2BU_ERR_SLICE_DESC: return "slice description array is truncated";
     case B2BU_ERR_ARGUMENT: return "invalid argument";
     case B2BU_ERR_CUDA: return "CUDA error";
+    case B2BU_ERR_NOMEM: return "out of host memory";
     default: return "unknown status";
     }
 }

@@ -238,6 +238,8 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
     DeviceCtx* c;
     int st = get_ctx(&c);
     if (st) return st;
+    // the handle's codebooks and scratch live on the device it was opened on: streams of another device's context cannot run on them
+    if (c->device != h->device) return B2BU_ERR_ARGUMENT;
     std::lock_guard<std::mutex> lk(h->mu);
     const size_t ns = slices.size();
     if (ns == 0) return B2BU_OK;
@@ -290,6 +292,15 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
     count_launch(1);
     CK(cudaEventRecord(h->ev[1], s));
 
+    // The verdict of every slice is read before anything is gathered: a resolver that stops at the first error leaves the rest
+    // of its slice's index plane unwritten (d_idx is grow-only scratch, never cleared), and K3 would index the codebooks with
+    // whatever is there.  A failed call therefore launches no gather and leaves the caller's buffer untouched (the reference
+    // returns Err and no image, basis_lz/mod.rs:97-186).  K2 runs for milliseconds; the extra synchronisation is noise.
+    std::vector<uint32_t> status(ns);
+    CK(cudaMemcpyAsync(status.data(), h->d_status, ns * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < ns; i++) if (status[i]) return (int)status[i];          // first failing slice in file order
+
     const uint32_t* idx = static_cast<const uint32_t*>(h->d_idx);
     if (target == B2BU_ETC1) {
         // images are the slices in order and ETC1 output does not depend on the slice shape: one gather over everything
@@ -308,14 +319,11 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
         }
     }
     CK(cudaEventRecord(h->ev[2], s));
-    std::vector<uint32_t> status(ns);
-    CK(cudaMemcpyAsync(status.data(), h->d_status, ns * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out, h->d_out, out_total, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(h->ev[3], s));
     CK(cudaStreamSynchronize(s));
     for (int i = 0; i < 3; i++) cudaEventElapsedTime(&h->last_ms[i], h->ev[i], h->ev[i + 1]);
     h->last_blocks = blocks_total; h->last_in_bytes = data_total; h->last_out_bytes = out_total;
-    for (size_t i = 0; i < ns; i++) if (status[i]) return (int)status[i];          // first failing slice in file order
     return B2BU_OK;
 }
 
@@ -325,7 +333,8 @@ static int etc1s_open_impl(uint32_t endpoint_count, uint32_t selector_count, con
     DeviceCtx* c;
     int st = get_ctx(&c);
     if (st) return st;
-    std::unique_ptr<b2bu_etc1s> h(new b2bu_etc1s);
+    struct Closer { void operator()(b2bu_etc1s* p) const { b2bu_etc1s_close(p); } };        // frees whatever was uploaded so far
+    std::unique_ptr<b2bu_etc1s, Closer> h(new b2bu_etc1s);
     h->device = c->device;
     h->num_endpoints = endpoint_count; h->num_selectors = selector_count; h->is_video = is_video;
 

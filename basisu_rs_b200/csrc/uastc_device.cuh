@@ -270,37 +270,6 @@ template <int WB> B2BU_DI uint32_t unquant_weight(uint32_t w)
     return r + (r >> 5);
 }
 
-// Two 8-bit channels in 16-bit lanes: ((l*257)*(64-w) + (h*257)*w + 32) >> 14 per lane
-// (uastc.rs:218-235 with srgb=false), using floor((257t+32)/2^14) == (t + ((t+32)>>8)) >> 6.
-B2BU_DI uint32_t lerp2(uint32_t lo, uint32_t hi, uint32_t w)
-{
-    const uint32_t t = lo * (64u - w) + hi * w;
-    const uint32_t u = t + (((t + 0x00200020u) >> 8) & 0x00FF00FFu);
-    return (u >> 6) & 0x00FF00FFu;
-}
-
-// Unquantised endpoints as packed pairs per subset: rb = R | B << 16, ga = G | A << 16 (uastc.rs:176-216)
-template <int M> struct Pairs { uint32_t lo_rb[MD<M>::subsets], hi_rb[MD<M>::subsets], lo_ga[MD<M>::subsets], hi_ga[MD<M>::subsets]; };
-
-template <int M> B2BU_DI void assemble_pairs(const uint32_t (&e)[MD<M>::N], Pairs<M>& p)
-{
-    using D = MD<M>;
-#pragma unroll
-    for (int s = 0; s < D::subsets; s++) {
-        const int o = s * D::NC * 2;
-        if (D::fmt == FMT_RGB) {
-            p.lo_rb[s] = e[o + 0] | (e[o + 4] << 16); p.hi_rb[s] = e[o + 1] | (e[o + 5] << 16);
-            p.lo_ga[s] = e[o + 2] | 0x00FF0000u;      p.hi_ga[s] = e[o + 3] | 0x00FF0000u;
-        } else if (D::fmt == FMT_RGBA) {
-            p.lo_rb[s] = e[o + 0] | (e[o + 4] << 16); p.hi_rb[s] = e[o + 1] | (e[o + 5] << 16);
-            p.lo_ga[s] = e[o + 2] | (e[o + 6] << 16); p.hi_ga[s] = e[o + 3] | (e[o + 7] << 16);
-        } else {
-            p.lo_rb[s] = e[o + 0] * 0x00010001u;      p.hi_rb[s] = e[o + 1] * 0x00010001u;
-            p.lo_ga[s] = e[o + 0] | (e[o + 2] << 16); p.hi_ga[s] = e[o + 1] | (e[o + 3] << 16);
-        }
-    }
-}
-
 template <int M> B2BU_DI void unpack_endpoints(const uint4& b, const DevTables& T, uint32_t (&e)[MD<M>::N])
 {
     uint32_t m[MD<M>::N], d[MD<M>::N];
@@ -313,15 +282,23 @@ template <int M> B2BU_DI void unpack_endpoints(const uint4& b, const DevTables& 
 // uastc.rs:237-327 decode_block_to_rgba, split in two so that the expensive half is ONE piece of
 // code shared by every mode (instruction-cache footprint: the 18 specialised copies of the texel
 // loop were 150 KB and thrashed the 32 KB L1.5 I-cache):
-//   canon_front<M>   mode-specialised, small: endpoints -> packed pairs, weights -> one byte per
-//                    texel, already unquantised to 0..64 (SWAR on the whole weight stream)
+//   canon_front<M>   mode-specialised, small: endpoints -> per-channel multiplier / offset words,
+//                    weights -> one byte per texel, already unquantised to 0..64 (SWAR on the
+//                    whole weight stream)
 //   interp_rows<>    mode-independent: 16 texels of ASTC interpolation from the canonical block
+//
+// The interpolation (uastc.rs:218-235 with srgb = false) is  ((l*257)*(64-w) + (h*257)*w + 32) >> 14.
+// Written as  l*257*64 + 32 + (h-l)*257*w  and scaled by 4 it is ONE multiply-add per channel and texel,
+//   r = D*w + L,   D = (h - l) * 1028 (two's complement),   L = l * 65792 + 128,
+// whose byte 2 (bits 16-23) is the result: r = 4 * (numerator), numerator >> 14 <= 255.  The multiply-adds
+// issue on the fma pipe, which the bit-twiddling rest of the kernel leaves mostly idle; the alu pipe only
+// sees the weight-byte extract and three byte permutes per texel.
 // ------------------------------------------------------------------------------------------
 struct Canon {
-    uint32_t lo_rb[3], hi_rb[3], lo_ga[3], hi_ga[3];   // endpoint pairs per subset: rb = R | B << 16, ga = G | A << 16
-    uint4 w0, w1;                                      // unquantised weights of plane 0 / 1, one byte per texel
-    uint32_t pw;                                       // subset map, 2 bits per texel
-    uint32_t mrb, mga;                                 // 16-bit lanes that take plane 1
+    uint32_t d[3][4], l[3][4];     // per subset and output channel R, G, B, A.  Dual plane (always one subset): d[1] is the
+                                   // multiplier of the plane-1 weight (non-zero for the selected channel only, where d[0] is zero)
+    uint4 w0, w1;                  // unquantised weights of plane 0 / 1, one byte per texel
+    uint32_t pw;                   // subset map, 2 bits per texel
 };
 
 // ASTC weight unquantisation (uastc.rs:697-719) on four byte lanes at once
@@ -355,63 +332,77 @@ template <int WB, int PLANES> B2BU_DI uint32_t weight_bytes4(const uint4& U, int
     return unquant_weight4<WB>(t);
 }
 
+// multiplier / offset words of one channel with endpoints l, h (see above)
+B2BU_DI uint32_t lerp_mul(uint32_t l, uint32_t h) { return (h - l) * 1028u; }
+B2BU_DI uint32_t lerp_off(uint32_t l) { return l * 65792u + 128u; }
+
 template <int M> B2BU_DI void canon_front(const uint4& b, const DevTables& T, uint32_t pat, uint32_t compsel, Canon& c)
 {
     using D = MD<M>;
     uint32_t e[D::N];
     unpack_endpoints<M>(b, T, e);
-    Pairs<M> p;
-    assemble_pairs<M>(e, p);
+    // uastc.rs:176-216 assemble_endpoint_pairs: RGB -> A = 255, LA -> L replicated to R, G, B
 #pragma unroll
-    for (int s = 0; s < 3; s++) {
-        const int q = s < D::subsets ? s : 0;
-        c.lo_rb[s] = p.lo_rb[q]; c.hi_rb[s] = p.hi_rb[q]; c.lo_ga[s] = p.lo_ga[q]; c.hi_ga[s] = p.hi_ga[q];
+    for (int s = 0; s < D::subsets; s++) {
+        const int o = s * D::NC * 2;
+        if (D::fmt == FMT_LA) {
+            c.d[s][0] = c.d[s][1] = c.d[s][2] = lerp_mul(e[o], e[o + 1]); c.l[s][0] = c.l[s][1] = c.l[s][2] = lerp_off(e[o]);
+            c.d[s][3] = lerp_mul(e[o + 2], e[o + 3]); c.l[s][3] = lerp_off(e[o + 2]);
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) { c.d[s][ch] = lerp_mul(e[o + 2 * ch], e[o + 2 * ch + 1]); c.l[s][ch] = lerp_off(e[o + 2 * ch]); }
+            if (D::fmt == FMT_RGBA) { c.d[s][3] = lerp_mul(e[o + 6], e[o + 7]); c.l[s][3] = lerp_off(e[o + 6]); }
+            else { c.d[s][3] = 0u; c.l[s][3] = lerp_off(255u); }
+        }
     }
     const uint4 U = uniform_weights<M>(b, T, pat);
     c.w0 = make_uint4(weight_bytes4<D::wbits, D::planes>(U, 0, 0), weight_bytes4<D::wbits, D::planes>(U, 1, 0),
                       weight_bytes4<D::wbits, D::planes>(U, 2, 0), weight_bytes4<D::wbits, D::planes>(U, 3, 0));
-    if (D::planes == 2)
+    if (D::planes == 2) {
         c.w1 = make_uint4(weight_bytes4<D::wbits, D::planes>(U, 0, 1), weight_bytes4<D::wbits, D::planes>(U, 1, 1),
                           weight_bytes4<D::wbits, D::planes>(U, 2, 1), weight_bytes4<D::wbits, D::planes>(U, 3, 1));
-    else c.w1 = c.w0;
-    c.pw = pattern_word<M>(T, pat);
-    c.mrb = 0u; c.mga = 0u;
-    if (D::planes == 2) {
-        c.mrb = compsel == 0u ? 0x0000FFFFu : compsel == 2u ? 0xFFFF0000u : 0u;
-        c.mga = compsel == 1u ? 0x0000FFFFu : compsel == 3u ? 0xFFFF0000u : 0u;
+        // the channel `compsel` follows plane 1 (uastc.rs:296-313): its multiplier moves to d[1]
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) { const bool sel = compsel == (uint32_t)ch; c.d[1][ch] = sel ? c.d[0][ch] : 0u; c.d[0][ch] = sel ? 0u : c.d[0][ch]; }
     }
+    c.pw = pattern_word<M>(T, pat);
 }
 
-// ((l*257)*(64-w) + (h*257)*w + 32) >> 14 on two 16-bit lanes, returned still shifted left by 6:
-// the caller takes bytes 0 and 2 of (result >> 6) with one byte permute
-B2BU_DI uint32_t lerp2_raw(uint32_t lo, uint32_t hi, uint32_t w, uint32_t iw)
+// r[ch] = d[ch] * w + l[ch] for the four channels when `on` is non-zero: four PREDICATED multiply-adds under one predicate.
+// (Left to the compiler, `if (subset == 1) r = ...` becomes a divergent branch per texel.)
+B2BU_DI void mad4_if(uint32_t (&r)[4], uint32_t on, const uint32_t (&d)[4], uint32_t w, const uint32_t (&l)[4])
 {
-    const uint32_t t = lo * iw + hi * w;
-    return t + __byte_perm(t + 0x00200020u, 0u, 0x4341);        // ((t + 32) >> 8) per 16-bit lane: bytes 1 and 3 moved down, one PRMT
+#ifdef B2BU_HOST_EMU
+    if (on) for (int ch = 0; ch < 4; ch++) r[ch] = d[ch] * w + l[ch];
+#else
+    asm("{\n.reg .pred p;\nsetp.ne.u32 p, %4, 0;\n"
+        "@p mad.lo.u32 %0, %5, %9, %10;\n@p mad.lo.u32 %1, %6, %9, %11;\n@p mad.lo.u32 %2, %7, %9, %12;\n@p mad.lo.u32 %3, %8, %9, %13;\n}\n"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3])
+        : "r"(on), "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]), "r"(w), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]));
+#endif
 }
 
-// One row of four texels.  MULTI: more than one subset; DUAL: two weight planes.
-template <bool MULTI, bool DUAL>
+// One row of four texels.  NSUB: subsets (1..3); DUAL: two weight planes (one subset).
+template <int NSUB, bool DUAL>
 B2BU_DI uint4 interp_row(const Canon& c, uint32_t wr0, uint32_t wr1, uint32_t pwr)
 {
     uint32_t px[4];
 #pragma unroll
     for (int x = 0; x < 4; x++) {
-        uint32_t lrb = c.lo_rb[0], hrb = c.hi_rb[0], lga = c.lo_ga[0], hga = c.hi_ga[0];
-        if (MULTI) {
-            const uint32_t s = (pwr >> (2 * x)) & 3u;
-            if (s == 1u) { lrb = c.lo_rb[1]; hrb = c.hi_rb[1]; lga = c.lo_ga[1]; hga = c.hi_ga[1]; }
-            if (s == 2u) { lrb = c.lo_rb[2]; hrb = c.hi_rb[2]; lga = c.lo_ga[2]; hga = c.hi_ga[2]; }
-        }
-        const uint32_t w = (wr0 >> (8 * x)) & 0xFFu, iw = 64u - w;
-        uint32_t rb = lerp2_raw(lrb, hrb, w, iw), ga = lerp2_raw(lga, hga, w, iw);
+        const uint32_t w = __byte_perm(wr0, 0u, 0x4440 + x);
+        uint32_t r[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) r[ch] = c.d[0][ch] * w + c.l[0][ch];
         if (DUAL) {
-            const uint32_t v = (wr1 >> (8 * x)) & 0xFFu, iv = 64u - v;
-            const uint32_t rb1 = lerp2_raw(lrb, hrb, v, iv), ga1 = lerp2_raw(lga, hga, v, iv);
-            rb = (rb & ~c.mrb) | (rb1 & c.mrb);
-            ga = (ga & ~c.mga) | (ga1 & c.mga);
+            const uint32_t v = __byte_perm(wr1, 0u, 0x4440 + x);
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) r[ch] += c.d[1][ch] * v;
         }
-        px[x] = __byte_perm(rb >> 6, ga >> 6, 0x6240);           // R, G, B, A
+        // subsets 1 / 2 (the map holds 0..2: bit 0 / bit 1 of the texel's field) overwrite the result of subset 0
+        if (NSUB >= 2) mad4_if(r, pwr & (1u << (2 * x)), c.d[1], w, c.l[1]);
+        if (NSUB == 3) mad4_if(r, pwr & (2u << (2 * x)), c.d[2], w, c.l[2]);
+        // byte 2 of every channel word -> R, G, B, A
+        px[x] = __byte_perm(__byte_perm(r[0], r[1], 0x0062), __byte_perm(r[2], r[3], 0x0062), 0x5410);
     }
     return make_uint4(px[0], px[1], px[2], px[3]);
 }
@@ -440,25 +431,25 @@ struct TileRowSink {
     B2BU_DI void row(int y, const uint4& v) { if (y == 0) *row0 = v; else rows123[(uint64_t)(y - 1) * stride] = v; }
 };
 
-template <bool MULTI, bool DUAL, class Sink> B2BU_DI void interp_rows(Canon& c, Sink& sink)
+template <int NSUB, bool DUAL, class Sink> B2BU_DI void interp_rows(Canon& c, Sink& sink)
 {
     if (Sink::ROLLED) {
 #pragma unroll 1
         for (int y = 0; y < 4; y++) {
-            sink.row(y, interp_row<MULTI, DUAL>(c, c.w0.x, c.w1.x, c.pw));
+            sink.row(y, interp_row<NSUB, DUAL>(c, c.w0.x, c.w1.x, c.pw));
             c.w0.x = c.w0.y; c.w0.y = c.w0.z; c.w0.z = c.w0.w;
             if (DUAL) { c.w1.x = c.w1.y; c.w1.y = c.w1.z; c.w1.z = c.w1.w; }
             c.pw >>= 8;
         }
     } else {
-        sink.row(0, interp_row<MULTI, DUAL>(c, c.w0.x, c.w1.x, c.pw));
-        sink.row(1, interp_row<MULTI, DUAL>(c, c.w0.y, c.w1.y, c.pw >> 8));
-        sink.row(2, interp_row<MULTI, DUAL>(c, c.w0.z, c.w1.z, c.pw >> 16));
-        sink.row(3, interp_row<MULTI, DUAL>(c, c.w0.w, c.w1.w, c.pw >> 24));
+        sink.row(0, interp_row<NSUB, DUAL>(c, c.w0.x, c.w1.x, c.pw));
+        sink.row(1, interp_row<NSUB, DUAL>(c, c.w0.y, c.w1.y, c.pw >> 8));
+        sink.row(2, interp_row<NSUB, DUAL>(c, c.w0.z, c.w1.z, c.pw >> 16));
+        sink.row(3, interp_row<NSUB, DUAL>(c, c.w0.w, c.w1.w, c.pw >> 24));
     }
 }
 
-// ---- SWAR helpers for the weight streams (palette path, BC7) -------------------------------
+// ---- SWAR helpers for the weight streams (BC7) ----------------------------------------------
 // 8 fields of 2 bits (16 bits) -> 8 nibble-spaced fields (32 bits)
 B2BU_DI uint32_t spread2to4(uint32_t x)
 {
@@ -482,128 +473,15 @@ B2BU_DI uint32_t compress4to2(uint32_t x)
     return (x | (x >> 8)) & 0x0000FFFFu;
 }
 
-// ------------------------------------------------------------------------------------------
-// Palette path of decode_block_to_rgba for the modes whose texels can only take <= 8 different values per
-// channel: 1 subset with 1-3 weight bits (modes 1, 5, 12, 14), 2 subsets with 2 weight bits (4, 7, 9, 16) and the
-// dual-plane modes (6, 11, 13, 17; each channel follows one plane).  The front-end interpolates the <= 8 values of
-// every channel once (two levels per multiply in 16-bit lanes, constant level weights), keeps them as byte vectors,
-// and the shared row code is then pure byte permutes: one PRMT looks up a channel for four texels, eight more
-// interleave R, G, B, A.  ~230 instead of ~500 instructions per block.
-// ------------------------------------------------------------------------------------------
-struct PalCanon {
-    uint32_t pal[4][2];        // per channel R, G, B, A: values of palette entries 0..3 and 4..7, one byte each
-    uint32_t x0[2], x1[2];     // palette index per texel (plane 0 / plane 1), one nibble per texel
-    uint32_t sel_plane1;       // dual plane: the channel (0..3) that follows plane 1
-};
-
-#ifndef B2BU_PALETTE
-#define B2BU_PALETTE 0      // measured on B200: 15 % fewer instructions but 14 % slower (hot code grows past the I-cache), so off
-#endif
-constexpr uint32_t kPaletteModes = B2BU_PALETTE ? ((1u << 1) | (1u << 5) | (1u << 12) | (1u << 14) | (1u << 4) | (1u << 7) | (1u << 9) | (1u << 16) |
-                                                   (1u << 6) | (1u << 11) | (1u << 13) | (1u << 17)) : 0u;
-__host__ __device__ constexpr bool is_palette_mode(int m) { return (kPaletteModes >> m) & 1u; }
-
-// unquantised level weights (uastc.rs:697-719)
-__host__ __device__ constexpr uint32_t level_weight(int wbits, int j)
-{
-    return wbits == 1 ? (j ? 64u : 0u) : wbits == 2 ? (j == 0 ? 0u : j == 1 ? 21u : j == 2 ? 43u : 64u)
-                                       : (j == 0 ? 0u : j == 1 ? 9u : j == 2 ? 18u : j == 3 ? 27u : j == 4 ? 37u : j == 5 ? 46u : j == 6 ? 55u : 64u);
-}
-
-// four consecutive palette entries (levels j0 .. j0+3 of a WB-bit weight) of one channel with endpoints l, h
-template <int WB> B2BU_DI uint32_t palette4(uint32_t l, uint32_t h, int j0)
-{
-    uint32_t v[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const uint32_t wa = level_weight(WB, j0 + 2 * k), wb = level_weight(WB, j0 + 2 * k + 1);
-        const uint32_t t = l * ((64u - wa) | ((64u - wb) << 16)) + h * (wa | (wb << 16));
-        v[k] = (t + (((t + 0x00200020u) >> 8) & 0x00FF00FFu)) >> 6;
-    }
-    return __byte_perm(v[0], v[1], 0x6420);
-}
-
-template <int M> B2BU_DI void pal_front(const uint4& b, const DevTables& T, uint32_t pat, uint32_t compsel, PalCanon& c)
-{
-    using D = MD<M>;
-    uint32_t e[D::N];
-    unpack_endpoints<M>(b, T, e);
-    // ---- palettes ----
-#pragma unroll
-    for (int ch = 0; ch < 4; ch++) { c.pal[ch][0] = 0xFFFFFFFFu; c.pal[ch][1] = 0xFFFFFFFFu; }      // RGB modes: A = 255
-#pragma unroll
-    for (int s = 0; s < D::subsets; s++) {
-        const int o = s * D::NC * 2;
-#pragma unroll
-        for (int q = 0; q < D::NC; q++) {                      // stored channel pairs: RGB(A) or L, A
-            const uint32_t l = e[o + 2 * q], h = e[o + 2 * q + 1];
-            uint32_t p0, p1 = 0;
-            if (D::wbits == 1) p0 = l | (h << 8);
-            else if (D::wbits == 2) p0 = palette4<2>(l, h, 0);
-            else { p0 = palette4<3>(l, h, 0); p1 = palette4<3>(l, h, 4); }
-            const int ch = D::fmt == FMT_LA ? (q == 0 ? 0 : 3) : q;
-            if (D::subsets == 2) c.pal[ch][s] = p0;              // entry = subset << 2 | weight
-            else { c.pal[ch][0] = p0; c.pal[ch][1] = p1; }
-        }
-    }
-    if (D::fmt == FMT_LA) {
-#pragma unroll
-        for (int k = 0; k < 2; k++) { c.pal[1][k] = c.pal[0][k]; c.pal[2][k] = c.pal[0][k]; }
-    }
-    // ---- palette index per texel ----
-    const uint4 U = uniform_weights<M>(b, T, pat);
-    c.sel_plane1 = 4u;
-    if (D::planes == 1) {
-        if (D::wbits == 2) { c.x0[0] = spread2to4(U.x & 0xFFFFu); c.x0[1] = spread2to4(U.x >> 16); }
-        else { c.x0[0] = spread3to4(U.x & 0xFFFFFFu); c.x0[1] = spread3to4(getbits(U, 24, 24)); }
-        if (D::subsets == 2) {
-            const uint32_t pw = pattern_word<M>(T, pat);
-            c.x0[0] |= spread2to4(pw & 0xFFFFu) << 2; c.x0[1] |= spread2to4(pw >> 16) << 2;
-        }
-        c.x1[0] = c.x0[0]; c.x1[1] = c.x0[1];
-    } else {
-        if (D::wbits == 2) {                                     // texel-major, plane-minor 2-bit fields
-            c.x0[0] = U.x & 0x33333333u; c.x0[1] = U.y & 0x33333333u;
-            c.x1[0] = (U.x >> 2) & 0x33333333u; c.x1[1] = (U.y >> 2) & 0x33333333u;
-        } else {                                                 // mode 13: 1-bit weights
-            const uint32_t a = spread2to4(U.x & 0xFFFFu), d = spread2to4(U.x >> 16);
-            c.x0[0] = a & 0x11111111u; c.x0[1] = d & 0x11111111u;
-            c.x1[0] = (a >> 1) & 0x11111111u; c.x1[1] = (d >> 1) & 0x11111111u;
-        }
-        c.sel_plane1 = compsel;
-    }
-}
-
-// four texels of one row from the palettes: sel0 / sel1 = four palette-index nibbles (plane 0 / plane 1)
-template <bool DUAL> B2BU_DI uint4 pal_row(const PalCanon& c, uint32_t sel0, uint32_t sel1)
-{
-    uint32_t ch4[4];
-#pragma unroll
-    for (int ch = 0; ch < 4; ch++) {
-        const uint32_t sel = DUAL ? (c.sel_plane1 == (uint32_t)ch ? sel1 : sel0) : sel0;
-        ch4[ch] = __byte_perm(c.pal[ch][0], c.pal[ch][1], sel);
-    }
-    const uint32_t rg01 = __byte_perm(ch4[0], ch4[1], 0x5140), rg23 = __byte_perm(ch4[0], ch4[1], 0x7362);
-    const uint32_t ba01 = __byte_perm(ch4[2], ch4[3], 0x5140), ba23 = __byte_perm(ch4[2], ch4[3], 0x7362);
-    return make_uint4(__byte_perm(rg01, ba01, 0x5410), __byte_perm(rg01, ba01, 0x7632), __byte_perm(rg23, ba23, 0x5410), __byte_perm(rg23, ba23, 0x7632));
-}
-
-template <bool DUAL, class Sink> B2BU_DI void pal_rows(const PalCanon& c, Sink& sink)
-{
-    sink.row(0, pal_row<DUAL>(c, c.x0[0], c.x1[0]));
-    sink.row(1, pal_row<DUAL>(c, c.x0[0] >> 16, c.x1[0] >> 16));
-    sink.row(2, pal_row<DUAL>(c, c.x0[1], c.x1[1]));
-    sink.row(3, pal_row<DUAL>(c, c.x0[1] >> 16, c.x1[1] >> 16));
-}
-
-constexpr uint32_t kMultiSubsetModes = (1u << 2) | (1u << 3) | (1u << 4) | (1u << 7) | (1u << 9) | (1u << 16);
+constexpr uint32_t kTwoSubsetModes = (1u << 2) | (1u << 4) | (1u << 7) | (1u << 9) | (1u << 16);
 constexpr uint32_t kDualPlaneModes = (1u << 6) | (1u << 11) | (1u << 13) | (1u << 17);
 
 template <class Sink> B2BU_DI void interp_block(uint32_t mode, Canon& c, Sink& sink)
 {
-    if ((kDualPlaneModes >> mode) & 1u) interp_rows<false, true>(c, sink);
-    else if ((kMultiSubsetModes >> mode) & 1u) interp_rows<true, false>(c, sink);
-    else interp_rows<false, false>(c, sink);
+    if ((kDualPlaneModes >> mode) & 1u) interp_rows<1, true>(c, sink);
+    else if (mode == 3u) interp_rows<3, false>(c, sink);
+    else if ((kTwoSubsetModes >> mode) & 1u) interp_rows<2, false>(c, sink);
+    else interp_rows<1, false>(c, sink);
 }
 
 // void-extent colour (uastc.rs:387-394): bits 5..36
@@ -1313,26 +1191,21 @@ B2BU_DI uint32_t transcode_mode_sink(uint32_t mode, const uint4& b, const DevTab
         return ERR_OK;
     }
     // RGBA, ETC1, ETC2: mode-specialised front-end, then texel code shared by all modes of a class
-    // (palette modes: byte-permute lookups; the rest: canonical block + interpolation)
     EtcFlags f;
     Canon c;
-    PalCanon pc;
-    const bool palette = (kPaletteModes >> mode) & 1u;
     switch (mode) {
 #define X(M) case M: if (!header_ok<M>(b, pat, compsel)) return ERR_PATTERN; \
                      if (TARGET != TGT_RGBA) f = read_trans_flags<M>(b); \
-                     if (is_palette_mode(M)) pal_front<M>(b, T, pat, compsel, pc); else canon_front<M>(b, T, pat, compsel, c); break;
+                     canon_front<M>(b, T, pat, compsel, c); break;
         B2BU_FOR_EACH_MODE(X)
 #undef X
     default: return ERR_MODE;
     }
     if (TARGET == TGT_RGBA) {
-        if (palette) { if ((kDualPlaneModes >> mode) & 1u) pal_rows<true>(pc, sink); else pal_rows<false>(pc, sink); }
-        else interp_block(mode, c, sink);
+        interp_block(mode, c, sink);
     } else {
         PxArraySink ps{o.px};
-        if (palette) { if ((kDualPlaneModes >> mode) & 1u) pal_rows<true>(pc, ps); else pal_rows<false>(pc, ps); }
-        else interp_block(mode, c, ps);
+        interp_block(mode, c, ps);
         o.etc = etc1_block(o.px, f, T);
         if (TARGET == TGT_ETC2) { const uint2 a = etc2_alpha_block(o.px, f.etc2tm, T); o.v = make_uint4(a.x, a.y, o.etc.x, o.etc.y); }
     }

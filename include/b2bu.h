@@ -61,7 +61,8 @@ enum b2bu_status {
     B2BU_ERR_ALPHA_SLICES = 15, /* "File has alpha, but slice count is odd" etc.             basis.rs:19,30,35 */
     B2BU_ERR_SLICE_DESC = 16,   /* "Expected 23 byte slice desc at pos ..."                  basis.rs:350 */
     B2BU_ERR_ARGUMENT = 17,     /* bad argument to this C API (null pointer, short output buffer, bad target) */
-    B2BU_ERR_CUDA = 18          /* CUDA runtime failure or no device: see b2bu_last_cuda_error()           */
+    B2BU_ERR_CUDA = 18,         /* CUDA runtime failure or no device: see b2bu_last_cuda_error()           */
+    B2BU_ERR_NOMEM = 19         /* host allocation failed inside the library (a C ABI must not unwind)     */
 };
 
 const char* b2bu_error_string(int status);
@@ -192,7 +193,13 @@ int b2bu_crc16_dev(const void* d_data, size_t len, uint16_t crc, uint16_t* resul
 /* basis.rs:8,92,145,175,204,233 read_to_{rgba,etc1,etc2,uastc,astc,bc7}.
  * Call with out == NULL to size: fills header, images[0..min(n,max_images)) (offset/nbytes/w/h/
  * stride), *num_images and *out_needed without touching the GPU.  Call again with a buffer of
- * at least *out_needed bytes to transcode; image i's bytes are at out + images[i].offset. */
+ * at least *out_needed bytes to transcode; image i's bytes are at out + images[i].offset.
+ * Data CRC (basis.rs:9-13 checks it before anything else): files below 256 KiB are checked on the host in both
+ * calls.  For larger files the check runs on the GPU inside the TRANSCODING call; the sizing call does not read
+ * the payload at all, so it cannot report "Data CRC16 failed" -- and, so that the reference's error precedence
+ * still holds, it reports no error of the file BODY either (slice table, alpha pairing ...): it returns
+ * B2BU_OK with *num_images = 0 and *out_needed = 0, and the transcoding call (any out != NULL, out_cap may be 0)
+ * delivers the verdict, CRC first.  Header errors are reported by both calls. */
 int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header, b2bu_image* images,
                  uint32_t max_images, uint32_t* num_images, uint8_t* out, uint64_t out_cap, uint64_t* out_needed);
 

@@ -72,6 +72,53 @@ def test_sizing_call_of_a_large_file_leaves_the_data_crc_to_the_decoding_call():
     assert L.b2bu_read_to(b.UASTC, g, len(g), None, imgs, 1, ctypes.byref(cnt), out, need.value, ctypes.byref(need)) == 12
 
 
+def _patch_header(f: bytes, **fields) -> bytes:
+    """rewrites header fields of a .basis file and re-signs the header CRC (basis.rs:419-454 layout)"""
+    import struct
+    from basis_writer import _crc16_fast
+    g = bytearray(f)
+    if "total_slices" in fields:
+        g[14:17] = struct.pack("<I", fields["total_slices"])[:3]
+    if "slice_desc_file_ofs" in fields:
+        g[65:69] = struct.pack("<I", fields["slice_desc_file_ofs"])
+    g[6:8] = struct.pack("<H", _crc16_fast(bytes(g[8:77])))
+    return bytes(g)
+
+
+def test_sizing_call_of_a_large_file_defers_body_errors_behind_the_crc():
+    """basis.rs:9-13 checks the data CRC before the slice table is looked at.  The sizing call of a large file does not read the
+    payload, so it must not report a body error either (it would take precedence over "Data CRC16 failed"): it returns OK
+    with no images, and the transcoding call delivers the verdict.  Small files report everything from the sizing call."""
+    import basisu_rs_b200 as b
+    from basis_writer import uastc_file
+    L = b.lib()
+    cnt, need = ctypes.c_uint32(7), ctypes.c_uint64(7)
+    big = np.zeros((160 * 128, 16), dtype=np.uint8).tobytes()
+    g = _patch_header(uastc_file(big, 160, 128, corrupt="data"), slice_desc_file_ofs=len(big) + 4096)     # bad CRC AND bad slice table
+    assert L.b2bu_read_to(b.BC7, g, len(g), None, None, 0, ctypes.byref(cnt), None, 0, ctypes.byref(need)) == 0
+    assert (cnt.value, need.value) == (0, 0)
+    small = np.zeros((6, 16), dtype=np.uint8).tobytes()
+    g = _patch_header(uastc_file(small, 3, 2), slice_desc_file_ofs=4096)
+    # the data CRC covers everything after the header, so patching the header keeps it valid: the body error shows
+    assert L.b2bu_read_to(b.BC7, g, len(g), None, None, 0, ctypes.byref(cnt), None, 0, ctypes.byref(need)) == 8
+
+
+def test_crafted_slice_count_does_not_allocate_or_unwind():
+    """total_slices is a 24-bit field of an unverified header: a 100-byte file claiming 16.7 M slices must fail with the
+    reference's slice-descriptor error, not with a 670 MB allocation or an exception through the C ABI."""
+    import resource
+    import basisu_rs_b200 as b
+    from basis_writer import uastc_file
+    L = b.lib()
+    cnt, need = ctypes.c_uint32(0), ctypes.c_uint64(0)
+    g = _patch_header(uastc_file(np.zeros((1, 16), dtype=np.uint8).tobytes(), 1, 1), total_slices=0xFFFFFF)
+    before = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    st = L.b2bu_read_to(b.BC7, g, len(g), None, None, 0, ctypes.byref(cnt), None, 0, ctypes.byref(need))
+    assert st in (8, 16)                                               # B2BU_ERR_RANGE / B2BU_ERR_SLICE_DESC
+    assert resource.getrusage(resource.RUSAGE_SELF).ru_maxrss - before < 64 * 1024      # KiB
+    assert L.b2bu_error_string(19) == b"out of host memory"
+
+
 def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
     import basisu_rs_b200 as b
     monkeypatch.setattr(b, "_LIB", None)

@@ -44,19 +44,6 @@ def test_kernel_source_error_codes(emu, oracle):
         assert (st >> 8, st & 0xFF) == (bad, e)
 
 
-@pytest.mark.parametrize("name", ["rgba", "etc1", "etc2"])
-def test_palette_variant_of_the_rgba_decode(emu_palette, oracle, kat, name):
-    """-DB2BU_PALETTE=1 (byte-permute palette lookups for the <= 8-level modes) is off in the product build because it
-    measured slower on B200, but it must stay bit-exact."""
-    t = TARGETS[name]
-    st, out = emu_transcode(emu_palette, t, kat.inputs)
-    assert st == 0xFFFFFFFFFFFFFFFF and (out.reshape(kat.n, OUT_BYTES[t]) == kat.expected[t]).all()
-    blk = random_blocks(30000, seed=21)
-    st, a = emu_transcode(emu_palette, t, blk, 100)
-    e, _, b = oracle_transcode(oracle, t, blk, 100)
-    assert st == 0xFFFFFFFFFFFFFFFF and e == 0 and (a == b).all()
-
-
 def test_eac_selector_threshold_rule_is_exhaustively_equal_to_the_reference_search():
     """uastc_device.cuh etc2_alpha_block replaces the reference's 8-candidate search (etc.rs:317-323, first minimum wins)
     by 7 threshold compares in value order.  Checked here for every table row, multiplier, centre and alpha value."""

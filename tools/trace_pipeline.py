@@ -11,21 +11,33 @@ from bench import make_payload, TARGET_NAMES, OUT_BYTES
 L = b.lib(); assert L.b2bu_init(0) == 0
 t = TARGET_NAMES[sys.argv[1]]; n = 2048 * 2048
 blk = make_payload("kat-shuffled", n)
-di = torch.from_numpy(blk.reshape(-1)).cuda(); do = torch.empty(n * OUT_BYTES[t], dtype=torch.uint8, device="cuda")
+if len(sys.argv) > 3:      # one UASTC mode only: the 32 golden blocks of that mode, tiled and shuffled (instruction-footprint experiment)
+    from conftest import Kat
+    k = Kat(); sel = k.inputs[k.modes == int(sys.argv[3])]
+    blk = np.ascontiguousarray(sel[np.random.default_rng(0).integers(0, len(sel), n)])
+# a ring of buffer sets larger than the L2, like bench.py: the traced launch reads its input from HBM
+ring = [(torch.from_numpy(np.roll(blk, 7 * i, axis=0).reshape(-1).copy()).cuda(), torch.empty(n * OUT_BYTES[t], dtype=torch.uint8, device="cuda")) for i in range(4)]
 st = torch.zeros(1, dtype=torch.int64, device="cuda"); L.b2bu_status_reset_dev(st.data_ptr(), None)
-for i in range(3):
+for i in range(7):
+    di, do = ring[i % 4]
     L.b2bu_uastc_transcode_dev(t, di.data_ptr(), n * 16, 2048, do.data_ptr(), n * OUT_BYTES[t], st.data_ptr(), None)
 torch.cuda.synchronize()
 L.b2bu_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
 L.b2bu_debug_trace(None, 1)
+di, do = ring[3]
 L.b2bu_uastc_transcode_dev(t, di.data_ptr(), n * 16, 2048, do.data_ptr(), n * OUT_BYTES[t], st.data_ptr(), None)
 torch.cuda.synchronize()
 tr = np.zeros((160, 64), dtype=np.uint64); L.b2bu_debug_trace(tr.ctypes.data, 0)
-for cta in (0, 73, 147):
+ends = (tr[:148, 59].astype(np.int64) - tr[:148, 60].astype(np.int64))
+print("DMA end per CTA (cycles after start): min %d median %d max %d; start skew %d" % (ends.min(), np.median(ends), ends.max(), int(tr[:148, 60].max() - tr[:148, 60].min())))
+order = np.argsort(ends)
+print("fastest CTAs:", [(int(c), int(ends[c])) for c in order[:6]])
+print("slowest CTAs:", [(int(c), int(ends[c])) for c in order[-12:]])
+print("waits of worker 0 (sorter, load) of the slowest:", [(int(tr[c, 61]), int(tr[c, 62])) for c in order[-6:]], "of the fastest:", [(int(tr[c, 61]), int(tr[c, 62])) for c in order[:6]])
+for cta in (0, 73, int(order[-1])):
     r = tr[cta].astype(np.int64); t0 = r[60]
-    print(f"CTA {cta}: worker0 end {r[63]-t0}, dma end {r[59]-t0}, wait(sorted) first worker {r[61]}, last worker {r[62]}")
-    print("  sorter phases tile 4 (warp0 / last warp), rel. to full:", [int(x - r[4*6+1]) for x in r[40:48]], [int(x - r[4*6+1]) for x in r[50:58]])
+    print(f"CTA {cta}: worker0 end {r[63]-t0}, dma end {r[59]-t0}; worker 0 waited {r[61]} cycles for the sorter, {r[62]} for the load")
     for k in range(6):
         v = r[k*6:k*6+5]
         if v[0] == 0: break
-        print(f"  tile {k}: load@{v[0]-t0} full@{v[1]-t0} sorted@{v[2]-t0} w0start@{v[3]-t0} w0done@{v[4]-t0}")
+        print(f"  tile {k}: load issued@{v[0]-t0} classified@{v[1]-t0} sorted@{v[2]-t0} w0start@{v[3]-t0} w0done@{v[4]-t0}")
