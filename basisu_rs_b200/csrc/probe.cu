@@ -9,6 +9,10 @@
 
 namespace b2bu {
 
+// Inline PTX on eight independent chains: the SASS holds exactly the counted instructions (LOP3.LUT with three register
+// inputs is ONE instruction; a C expression like (a ^ k1) & (b | k2) is two, which an earlier version of this probe counted
+// as one).  MIX = 0: alu pipe only (LOP3); MIX = 1: LOP3 and IMAD alternating, one per pipe (tools/probe_pipes.cu measures
+// every instruction kind the kernels use: 64 thread-instructions per clock per SM on either pipe, 128 on both together).
 template <int MIX>   // 0: alu pipe only, 1: alternate alu / fma pipe
 __global__ void __launch_bounds__(1024) int_probe_kernel(uint32_t* out, uint32_t iters, uint32_t seed)
 {
@@ -21,9 +25,9 @@ __global__ void __launch_bounds__(1024) int_probe_kernel(uint32_t* out, uint32_t
         for (int r = 0; r < 4; r++) {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                a[i] = (a[i] ^ k1) & (a[(i + 1) & 7] | k2);      // LOP3
-                if (MIX) a[i] = a[i] * k1 + k2;                  // IMAD
-                else a[i] = __funnelshift_l(a[i], a[(i + 3) & 7], 7);   // SHF (an integer add would be issued as IMAD.IADD on the fma pipe)
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(k1), "r"(k2));
+                if (MIX) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(k1), "r"(k2));
+                else asm volatile("lop3.b32 %0, %0, %1, %2, 0x69;" : "+r"(a[i]) : "r"(k2), "r"(k1));
             }
         }
     }
