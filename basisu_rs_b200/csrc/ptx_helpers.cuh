@@ -53,7 +53,7 @@ __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_group_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_group_0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // wait of a role that has nothing else to do for microseconds (the DMA lane waiting for a tile to be finished): polls with
 // a sleep in between, so that the waiting warp does not take issue slots from the warps it is waiting for

@@ -1,7 +1,9 @@
 // K1<target>: fused UASTC unpack + repack kernels.
 // One thread per 16-byte block, 128-bit coalesced loads and stores, constant tables in shared
 // memory.  Replaces uastc::Decoder::{transcode,decode_to_rgba} (reference src/uastc.rs:89-165).
+#include <atomic>
 #include <cstddef>
+#include <mutex>
 #include "uastc_device.cuh"
 #include "ptx_helpers.cuh"
 #include "kernels.h"
@@ -52,10 +54,10 @@ __device__ __forceinline__ uint32_t atom_add_shared(uint32_t* p, uint32_t v)
 
 // predicated forms (straight-line code: left to the compiler, a conditional atomic or store becomes a branch region per use)
 // (each takes the two sides of its condition  a < b  so that the predicate is one compare, not a materialised bool)
-__device__ __forceinline__ uint32_t atom_inc_shared_if_lt(uint32_t saddr, uint32_t a, uint32_t b)
+__device__ __forceinline__ uint32_t atom_inc_shared(uint32_t saddr)
 {
-    uint32_t old = 0u;
-    asm volatile("{\n.reg .pred p;\nsetp.lt.u32 p, %2, %3;\n@p atom.shared.add.u32 %0, [%1], 1;\n}\n" : "+r"(old) : "r"(saddr), "r"(a), "r"(b));
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(saddr));
     return old;
 }
 __device__ __forceinline__ void sts_u16_if_lt(uint32_t saddr, uint32_t v, uint32_t a, uint32_t b)
@@ -166,10 +168,7 @@ template <int TARGET> struct PipeCfg {
     static constexpr bool IN_PLACE = OB == 16;
     static constexpr int NS = 2;                   // data slots: one being worked on, one being stored / loaded
     static constexpr int NO = B2BU_ORDER_SLOTS;    // order slots: how far the sorter may run ahead
-#ifndef B2BU_ASTC_DYNAMIC
-#define B2BU_ASTC_DYNAMIC 0
-#endif
-    static constexpr bool DYNAMIC = TARGET != TGT_ASTC || B2BU_ASTC_DYNAMIC;
+    static constexpr bool DYNAMIC = TARGET != TGT_ASTC;
     static constexpr int TILE = TARGET == TGT_RGBA ? B2BU_TILE_RGBA : TARGET == TGT_ETC1 ? B2BU_TILE_ETC1 : B2BU_TILE16;
     static constexpr int SORT_WARPS = B2BU_SORT_WARPS;
     static constexpr int SORT_THREADS = SORT_WARPS * 32;
@@ -190,25 +189,35 @@ template <int TARGET> struct PipeCfg {
     static constexpr size_t OFF_WCNT = OFF_STAGE + 2 * (size_t)STAGE * 4;
     static constexpr size_t OFF_BASE = OFF_WCNT + (size_t)SORT_WARPS * 32 * 4;
     static constexpr size_t OFF_CTL = OFF_BASE + (size_t)SORT_WARPS * 32 * 4;
-    static constexpr size_t OFF_BAR = (OFF_CTL + NO * 2 * 4 + 7) / 8 * 8;
+    static constexpr int ND = 8;                   // tile descriptors in flight (first block, blocks): sorter -> DMA lane, workers
+    static constexpr size_t OFF_DESC = (OFF_CTL + NO * 2 * 4 + 7) / 8 * 8;
+    static constexpr size_t OFF_BAR = OFF_DESC + ND * 8 + 8;
+    static constexpr int TMIN = TILE / 4;          // smallest tile handed out (the bins are padded to 32 blocks each: small tiles waste lanes)
     static constexpr size_t SMEM = OFF_BAR + (2 * NS + 2 * NO) * 8;
     static_assert(SMEM <= 227 * 1024, "tile configuration does not fit shared memory");
     static_assert(THREADS <= 1024, "too many warps");
     static_assert((SORT_THREADS & (SORT_THREADS - 1)) == 0, "the sorter's block permutation needs a power of two");
+    static_assert(ND >= NO + NS + 2, "a descriptor must outlive the store of its tile");
 };
 
-// contiguous, 32-block aligned share of CTA c out of G
-// (quot, rem) = (nblocks / G, nblocks % G) come from the host
-__device__ __forceinline__ uint64_t cta_range_start(uint64_t nblocks, uint64_t quot, uint32_t rem, uint32_t c, uint32_t G)
+// Tiles are handed out DYNAMICALLY: the CTAs of a launch draw block ranges from one global cursor (sched[0]).  Equal static
+// shares left the slowest SM 15 % behind the median (identical work, different instruction-fetch and memory latencies), and
+// the launch lasts as long as its slowest CTA.  The first round hands every CTA a short tile (TILE/4) so that the workers start
+// early, then full tiles, and the last ~G tiles shrink towards TMIN (guided self-scheduling) so that the CTAs finish together
+// and the final stores, which nothing overlaps, are short.
+template <int TILE, int TMIN>
+__device__ __forceinline__ uint32_t chunk_want(uint32_t cur, uint32_t nblocks, uint32_t G)
 {
-    if (c >= G) return nblocks;
-    return (quot * c + rem * c / G) & ~31ull;
+    if (cur < G * (uint32_t)(TILE / 4)) return (uint32_t)(TILE / 4);
+    const uint32_t rem = nblocks > cur ? nblocks - cur : 0u;
+    const uint32_t w = (rem / G + 31u) & ~31u;
+    return w > (uint32_t)TILE ? (uint32_t)TILE : w < (uint32_t)TMIN ? (uint32_t)TMIN : w;
 }
 
 template <int TARGET>
 __global__ void __launch_bounds__(PipeCfg<TARGET>::THREADS, 1)
-uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64_t nblocks, uint32_t blocks_per_row,
-                    uint64_t index_base, unsigned long long* __restrict__ err, uint64_t range_quot, uint32_t range_rem)
+uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint32_t nblocks, uint32_t blocks_per_row,
+                    uint64_t index_base, unsigned long long* __restrict__ err, unsigned int* __restrict__ sched)
 {
     using C = PipeCfg<TARGET>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -221,36 +230,14 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
     uint32_t* wcnt = reinterpret_cast<uint32_t*>(smem + C::OFF_WCNT);         // [SORT_WARPS][32]
     uint32_t* wbase = reinterpret_cast<uint32_t*>(smem + C::OFF_BASE);        // [SORT_WARPS][32]
     uint32_t* ctl = reinterpret_cast<uint32_t*>(smem + C::OFF_CTL);           // [NO][2]: next item, number of items
+    uint2* tdesc = reinterpret_cast<uint2*>(smem + C::OFF_DESC);              // [ND] tile k: (first block, blocks); blocks == 0 ends the CTA
+    volatile uint32_t* desc_seq = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_DESC + C::ND * 8);   // descriptors published so far
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* bar_full = bars, *bar_done = bars + C::NS, *bar_sorted = bars + 2 * C::NS, *bar_ofree = bar_sorted + C::NO;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // this CTA's contiguous block range, cut into tiles of at most TILE blocks (multiples of 32).  The first two tiles are
-    // short (TILE/4, TILE/2) so that the workers start early, the last one is short (<= TILE/4) so that the final store,
-    // which nothing overlaps, is short; the rest of the range is cut into equal tiles.
-    const uint64_t r0 = cta_range_start(nblocks, range_quot, range_rem, blockIdx.x, gridDim.x);
-    const uint64_t r1 = cta_range_start(nblocks, range_quot, range_rem, blockIdx.x + 1, gridDim.x);
-    const uint32_t rlen = (uint32_t)(r1 - r0);
-    const uint32_t a0 = rlen < (uint32_t)C::TILE / 4 ? rlen : (uint32_t)C::TILE / 4;
-    const uint32_t a1 = rlen - a0 < (uint32_t)C::TILE / 2 ? rlen - a0 : (uint32_t)C::TILE / 2;
-    const uint32_t after = rlen - a0 - a1;
-    // start of the short last tile (32-block aligned like every tile start: ETC1's bulk stores need even block indices)
-    const uint32_t mid_end = after > (uint32_t)C::TILE ? ((rlen - (uint32_t)C::TILE / 4) & ~31u) : rlen;
-    const uint32_t zlast = rlen - mid_end;
-    const uint32_t rest = mid_end - a0 - a1;
-    const uint32_t nrest = (rest + C::TILE - 1) / C::TILE;
-    const uint32_t tsz = nrest ? (((rest + nrest - 1) / nrest + 31u) & ~31u) : 0u;
-    const uint32_t ntiles = (a0 ? 1u : 0u) + (a1 ? 1u : 0u) + nrest + (zlast ? 1u : 0u);
-    auto tile_start = [&](uint32_t k) -> uint32_t {
-        if (k == 0) return 0u;
-        if (k == 1) return a0;
-        if (k >= ntiles) return rlen;
-        const uint32_t o = a0 + a1 + (k - 2) * tsz;
-        return o < mid_end ? o : mid_end;
-    };
-    auto tile_blocks = [&](uint32_t k) -> uint32_t { return tile_start(k + 1) - tile_start(k); };
-
+    if (tid == 0) *desc_seq = 0u;
     if (tid == 0) {
         for (int i = 0; i < C::NS; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_done[i], C::WORK_WARPS); }
         for (int i = 0; i < C::NO; i++) { mbar_init(&bar_sorted[i], 1); mbar_init(&bar_ofree[i], C::WORK_WARPS); }
@@ -258,13 +245,16 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
     }
     load_tables(&T, TableBytes<TARGET>::value);  // ends with __syncthreads()
     if (tid == 0) TRACE(60);
+#ifdef B2BU_TRACE
+    if (tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_trace[blockIdx.x][57] = gt; }
+#endif
 
     if (warp == C::WORK_WARPS + C::SORT_WARPS) {
         // ================================ DMA warp ================================
         if (lane != 0) return;
         auto store_tile = [&](uint32_t k) {
-            const uint32_t s = k % C::NS, nt = tile_blocks(k);
-            const uint64_t g0 = r0 + tile_start(k);
+            const uint32_t s = k % C::NS, nt = tdesc[k % C::ND].y;
+            const uint64_t g0 = tdesc[k % C::ND].x;
             fence_async_smem();
             if (TARGET == TGT_RGBA) {
                 // four pixel rows per block row; a tile may span several block rows
@@ -291,24 +281,34 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
             }
             tma_store_commit();
         };
-        for (uint32_t k = 0; k < ntiles; k++) {
+        uint32_t k = 0;
+        for (;; k++) {
+            while (*desc_seq <= k) asm volatile("nanosleep.u32 100;");          // the sorter publishes tile k's descriptor
+            __threadfence_block();
+            const uint2 d = tdesc[k % C::ND];
+            if (d.y == 0u) break;                              // no more work for this CTA
             const uint32_t s = k % C::NS, u = k / C::NS;
             if (k >= (uint32_t)C::NS) {                        // slot reuse: tile k-NS must be finished and stored
                 mbar_wait_backoff(&bar_done[s], (u - 1u) & 1u, 200);
                 store_tile(k - C::NS);
                 tma_store_wait_read();
             }
-            const uint32_t bytes = tile_blocks(k) * 16u;
-            mbar_expect_tx(&bar_full[s], bytes);
-            tma_load_1d(in_s + s * C::TILE, in + r0 + tile_start(k), bytes, &bar_full[s]);
+            mbar_expect_tx(&bar_full[s], d.y * 16u);
+            tma_load_1d(in_s + s * C::TILE, in + d.x, d.y * 16u, &bar_full[s]);
             do { if (k < 6) TRACE(k * 6 + 0); } while (0);
         }
-        for (uint32_t k = ntiles >= (uint32_t)C::NS ? ntiles - C::NS : 0; k < ntiles; k++) {
-            mbar_wait_backoff(&bar_done[k % C::NS], (k / C::NS) & 1u, 200);
-            store_tile(k);
+        const uint32_t ntiles = k;
+        for (uint32_t j = ntiles >= (uint32_t)C::NS ? ntiles - C::NS : 0; j < ntiles; j++) {
+            mbar_wait_backoff(&bar_done[j % C::NS], (j / C::NS) & 1u, 200);
+            store_tile(j);
         }
         tma_store_wait_all();
         TRACE(59);
+#ifdef B2BU_TRACE
+        { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_trace[blockIdx.x][58] = gt; }
+#endif
+        // the last CTA of the launch to finish rewinds the cursor for the next launch that uses this slot
+        if (atomicInc(&sched[1], gridDim.x - 1u) == gridDim.x - 1u) sched[0] = 0u;
         return;
     }
 
@@ -327,23 +327,47 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
         // the 16 lane pairs fall on different even banks), which another thread has copied -- hence a barrier after the wait.
         auto blocks_of = [&](uint32_t nt, int first) -> uint32_t { return nt > (uint32_t)first ? (nt - (uint32_t)first + C::SORT_THREADS - 1) / C::SORT_THREADS : 0u; };
         auto prefetch = [&](uint32_t k) {
-            if (k < ntiles) {
-                const uint32_t myj = blocks_of(tile_blocks(k), st);
-                const uint4* src = in + r0 + tile_start(k) + st;
-                const uint32_t dst = smem_u32(stage + (k & 1u) * C::STAGE + st);
+            const uint2 d = tdesc[k % C::ND];
+            const uint32_t myj = blocks_of(d.y, st);          // 0 for the end marker
+            const uint4* src = in + d.x + st;
+            const uint32_t dst = smem_u32(stage + (k & 1u) * C::STAGE + st);
 #pragma unroll
-                for (int j = 0; j < C::PERS; j++) cp_async_4_if_lt(dst + j * C::SORT_THREADS * 4, src + j * C::SORT_THREADS, (uint32_t)j, myj);
-            }
-            cp_async_commit();                                  // one group per call, empty past the last tile
+            for (int j = 0; j < C::PERS; j++) cp_async_4_if_lt(dst + j * C::SORT_THREADS * 4, src + j * C::SORT_THREADS, (uint32_t)j, myj);
+            cp_async_commit();
         };
+        // thread 0 draws tile j's block range from the launch's cursor and publishes it; the other sorter threads may read it
+        // after the next named barrier, the DMA lane polls desc_seq, the workers read it behind bar_sorted
+        auto draw = [&](uint32_t j) {
+            if (st != 0) return;
+            uint2 d = make_uint2(0u, 0u);
+            const uint32_t cur = *reinterpret_cast<volatile unsigned int*>(&sched[0]);
+            if (cur < nblocks) {
+                const uint32_t want = chunk_want<C::TILE, C::TMIN>(cur, nblocks, gridDim.x);
+                const uint32_t pos = atomicAdd(&sched[0], want);
+                if (pos < nblocks) d = make_uint2(pos, nblocks - pos < want ? nblocks - pos : want);
+            }
+            tdesc[j % C::ND] = d;
+            __threadfence_block();
+            *desc_seq = j + 1u;
+        };
+        draw(0);
+        named_bar_sync(1, C::SORT_THREADS);
         prefetch(0);
-        for (uint32_t k = 0; k < ntiles; k++) {
-            const uint32_t o = k % C::NO, nt = tile_blocks(k);
-            prefetch(k + 1);
+        for (uint32_t k = 0;; k++) {
+            const uint32_t o = k % C::NO, nt = tdesc[k % C::ND].y;
+            if (nt == 0u) {
+                // end marker: hand it to the workers through the same barrier (behind the release of the order slot, so that no
+                // worker can still be waiting on the slot's previous phase)
+                if (k >= (uint32_t)C::NO) mbar_wait(&bar_ofree[o], (k / C::NO - 1u) & 1u);
+                if (st == 0) mbar_arrive(&bar_sorted[o]);
+                break;
+            }
+            draw(k + 1);
             mycnt[lane] = 0;
             __syncwarp();
-            cp_async_wait_group_1();                            // this thread's copies of tile k's words have landed
-            named_bar_sync(1, C::SORT_THREADS);                 // ... and everybody else's
+            cp_async_wait_group_0();                            // this thread's copies of tile k's words have landed
+            named_bar_sync(1, C::SORT_THREADS);                 // ... and everybody else's; tile k+1's descriptor is visible
+            prefetch(k + 1);
             // A: classify, rank inside (warp, mode).  Every step is a branch-free pass over all of the thread's blocks (PERS
             // loads / atomics in flight); blocks past the end of a short tile are predicated off.
             const uint32_t myj = blocks_of(nt, bst);            // passes j in which block bst + j * SORT_THREADS is inside the tile
@@ -352,7 +376,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
 #pragma unroll
             for (int j = 0; j < C::PERS; j++) mr[j] = src[j * C::SORT_THREADS] & 127u;      // stale words past the end: discarded below
 #pragma unroll
-            for (int j = 0; j < C::PERS; j++) mr[j] = T.mode_lut[mr[j]];
+            for (int j = 0; j < C::PERS; j++) { const uint32_t lut = T.mode_lut[mr[j]]; mr[j] = (uint32_t)j < myj ? lut : 31u; }   // 31: dummy bin
             // the order slot must have been consumed (tile k - NO)
             if (k >= (uint32_t)C::NO) mbar_wait(&bar_ofree[o], (k / C::NO - 1u) & 1u);
             if (st == 0) do { if (k < 6) TRACE(k * 6 + 1); } while (0);
@@ -362,7 +386,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
                 const uint32_t cnt_base = smem_u32(mycnt);
                 uint32_t rk[C::PERS];
 #pragma unroll
-                for (int j = 0; j < C::PERS; j++) rk[j] = atom_inc_shared_if_lt(cnt_base + 4u * mr[j], (uint32_t)j, myj);
+                for (int j = 0; j < C::PERS; j++) rk[j] = atom_inc_shared(cnt_base + 4u * mr[j]);   // straight-line: blocks past the end count into the dummy bin
 #pragma unroll
                 for (int j = 0; j < C::PERS; j++) mr[j] |= rk[j] << 8;
             }
@@ -411,17 +435,19 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
     }
 
     // ================================ worker warps ================================
-    for (uint32_t k = 0; k < ntiles; k++) {
+    for (uint32_t k = 0;; k++) {
         const uint32_t s = k % C::NS, o = k % C::NO;
         uint4* tin = in_s + s * C::TILE;
         unsigned char* tout = out_s + s * C::OUT_SLOT;
         const uint16_t* ord = order + o * C::MAXORD;
         const uint16_t* itm = items + o * C::MAXITEMS;
-        const uint64_t base = r0 + tile_start(k);
 #ifdef B2BU_TRACE
         const long long tw0 = clock64();
 #endif
         mbar_wait(&bar_sorted[o], (k / C::NO) & 1u);
+        const uint2 dk = tdesc[k % C::ND];
+        if (dk.y == 0u) break;                    // end marker
+        const uint64_t base = dk.x;
 #ifdef B2BU_TRACE
         const long long tw1 = clock64();
 #endif
@@ -434,6 +460,8 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
         // the SM inside the same few modes, i.e. the same few KB of code: dealing the items round-robin instead let the
         // warps drift apart and ran the large-code targets (ETC1/ETC2) 3x slower on instruction-cache misses.  ASTC's
         // code is small enough for the static deal to win (no counter round trip per item).
+        // (Claiming the NEXT item before the current one is processed hides the counter round trip but costs far more at the end
+        // of a tile, where a warp that is busy with a long item then sits on an item an idle warp could have taken: RGBA 97 -> 152 us.)
         for (uint32_t it = (uint32_t)warp;; it += C::WORK_WARPS) {
             uint32_t item = it;
             if (C::DYNAMIC) {
@@ -474,6 +502,32 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint64
     if (lane == 0 && warp == 0) TRACE(63);
 }
 
+// Cursor slots of the dynamic tile scheduler: {next block, CTAs finished} per launch in flight.  A launch takes the next slot of
+// a ring; the last CTA to finish rewinds the slot's cursor, so a slot is reusable as soon as its launch has ended (launches that
+// overlap in time -- different streams -- sit in different slots as long as fewer than kSchedSlots of them are in flight).
+constexpr unsigned kSchedSlots = 64, kSchedStride = 8;          // 32 bytes apart
+static unsigned int* g_sched[kMaxDevicesK] = {};
+static std::mutex g_sched_mu;
+static std::atomic<unsigned> g_sched_seq{0};
+
+static cudaError_t sched_slot(int dev, unsigned int** slot)
+{
+    if (dev < 0 || dev >= kMaxDevicesK) return cudaErrorInvalidDevice;
+    if (!g_sched[dev]) {
+        std::lock_guard<std::mutex> lk(g_sched_mu);
+        if (!g_sched[dev]) {
+            unsigned int* p = nullptr;
+            cudaError_t e = cudaMalloc(&p, kSchedSlots * kSchedStride * sizeof(unsigned int));
+            if (e != cudaSuccess) return e;
+            e = cudaMemset(p, 0, kSchedSlots * kSchedStride * sizeof(unsigned int));
+            if (e != cudaSuccess) { cudaFree(p); return e; }
+            g_sched[dev] = p;
+        }
+    }
+    *slot = g_sched[dev] + (g_sched_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots) * kSchedStride;
+    return cudaSuccess;
+}
+
 template <int TARGET>
 static cudaError_t launch_sorted(const uint4* in, void* d_out, uint64_t nblocks, uint32_t bpr, uint64_t index_base,
                                  unsigned long long* d_err, int sm_count, cudaStream_t stream)
@@ -487,12 +541,25 @@ static cudaError_t launch_sorted(const uint4* in, void* d_out, uint64_t nblocks,
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    // one persistent CTA per SM; fewer when the input is small (at least ~one half tile each)
-    const uint64_t want = (nblocks + C::TILE / 2 - 1) / (C::TILE / 2);
-    const uint64_t cap = (uint64_t)sm_count;
-    const unsigned grid = (unsigned)(want < cap ? want : cap);
-    uastc_sorted_kernel<TARGET><<<grid, C::THREADS, C::SMEM, stream>>>(in, d_out, nblocks, bpr, index_base, d_err, nblocks / grid, (uint32_t)(nblocks % grid));
-    return cudaGetLastError();
+    // the kernel counts blocks in 32 bits: larger inputs go in pieces (whole block rows for the row-major RGBA image)
+    const uint64_t unit = TARGET == TGT_RGBA ? (uint64_t)bpr : 32u;
+    const uint64_t piece_max = ((uint64_t)1 << 31) / unit * unit;
+    for (uint64_t done = 0; done < nblocks;) {
+        const uint64_t n = nblocks - done < piece_max ? nblocks - done : piece_max;
+        unsigned int* slot = nullptr;
+        cudaError_t e = sched_slot(dev, &slot);
+        if (e != cudaSuccess) return e;
+        // one persistent CTA per SM; fewer when the input is small (at least ~one first-round tile each)
+        const uint64_t want = (n + C::TILE / 4 - 1) / (C::TILE / 4);
+        const unsigned grid = (unsigned)(want < (uint64_t)sm_count ? want : (uint64_t)sm_count);
+        const size_t ob = (size_t)C::OB;
+        uastc_sorted_kernel<TARGET><<<grid, C::THREADS, C::SMEM, stream>>>(in + done, static_cast<unsigned char*>(d_out) + done * ob, (uint32_t)n, bpr,
+                                                                           index_base + done, d_err, slot);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        done += n;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_uastc_transcode(int target, const void* d_in, void* d_out, uint64_t nblocks, uint32_t blocks_per_row,

@@ -30,6 +30,9 @@ torch.cuda.synchronize()
 tr = np.zeros((160, 64), dtype=np.uint64); L.b2bu_debug_trace(tr.ctypes.data, 0)
 ends = (tr[:148, 59].astype(np.int64) - tr[:148, 60].astype(np.int64))
 print("DMA end per CTA (cycles after start): min %d median %d max %d; start skew %d" % (ends.min(), np.median(ends), ends.max(), int(tr[:148, 60].max() - tr[:148, 60].min())))
+g0, g1 = tr[:148, 57].astype(np.int64), tr[:148, 58].astype(np.int64)
+print("globaltimer (ns): CTA start spread %d, end spread %d, first start -> last end %d; per-CTA duration min %d median %d max %d" % (
+    g0.max() - g0.min(), g1.max() - g1.min(), g1.max() - g0.min(), (g1 - g0).min(), np.median(g1 - g0), (g1 - g0).max()))
 order = np.argsort(ends)
 print("fastest CTAs:", [(int(c), int(ends[c])) for c in order[:6]])
 print("slowest CTAs:", [(int(c), int(ends[c])) for c in order[-12:]])
