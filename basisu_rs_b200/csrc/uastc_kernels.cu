@@ -141,7 +141,7 @@ __constant__ uint8_t kBinOrder[32] = {3, 9, 16, 4, 7, 2, 12, 10, 11, 13, 14, 6, 
 #define B2BU_TILE_RGBA 1536
 #endif
 #ifndef B2BU_TILE_ETC1
-#define B2BU_TILE_ETC1 3072     // 8 B of staged output per block and slot beside the input
+#define B2BU_TILE_ETC1 3584     // 8 B of staged output per block and slot beside the input
 #endif
 #ifndef B2BU_SORT_WARPS
 #define B2BU_SORT_WARPS 8
@@ -150,7 +150,7 @@ __constant__ uint8_t kBinOrder[32] = {3, 9, 16, 4, 7, 2, 12, 10, 11, 13, 14, 6, 
 #define B2BU_WORK_WARPS 23
 #endif
 #ifndef B2BU_ORDER_SLOTS
-#define B2BU_ORDER_SLOTS 3
+#define B2BU_ORDER_SLOTS 2
 #endif
 
 #ifdef B2BU_TRACE
@@ -192,7 +192,6 @@ template <int TARGET> struct PipeCfg {
     static constexpr int ND = 8;                   // tile descriptors in flight (first block, blocks): sorter -> DMA lane, workers
     static constexpr size_t OFF_DESC = (OFF_CTL + NO * 2 * 4 + 7) / 8 * 8;
     static constexpr size_t OFF_BAR = OFF_DESC + ND * 8 + 8;
-    static constexpr int TMIN = TILE / 4;          // smallest tile handed out (the bins are padded to 32 blocks each: small tiles waste lanes)
     static constexpr size_t SMEM = OFF_BAR + (2 * NS + 2 * NO) * 8;
     static_assert(SMEM <= 227 * 1024, "tile configuration does not fit shared memory");
     static_assert(THREADS <= 1024, "too many warps");
@@ -203,15 +202,14 @@ template <int TARGET> struct PipeCfg {
 // Tiles are handed out DYNAMICALLY: the CTAs of a launch draw block ranges from one global cursor (sched[0]).  Equal static
 // shares left the slowest SM 15 % behind the median (identical work, different instruction-fetch and memory latencies), and
 // the launch lasts as long as its slowest CTA.  The first round hands every CTA a short tile (TILE/4) so that the workers start
-// early, then full tiles, and the last ~G tiles shrink towards TMIN (guided self-scheduling) so that the CTAs finish together
-// and the final stores, which nothing overlaps, are short.
-template <int TILE, int TMIN>
-__device__ __forceinline__ uint32_t chunk_want(uint32_t cur, uint32_t nblocks, uint32_t G)
+// early; after that every tile is a full one.  (Guided self-scheduling -- tiles that shrink towards the end of the launch so
+// that the CTAs finish together -- was measured and lost: a tile's fixed costs, the sort's barriers and the bins' padding to 32
+// blocks, weigh more on small tiles than the imbalance of at most one tile costs.  ASTC: full tiles 58 us, shrinking to a
+// quarter 60, to an eighth 66.)
+template <int TILE>
+__device__ __forceinline__ uint32_t chunk_want(uint32_t cur, uint32_t G)
 {
-    if (cur < G * (uint32_t)(TILE / 4)) return (uint32_t)(TILE / 4);
-    const uint32_t rem = nblocks > cur ? nblocks - cur : 0u;
-    const uint32_t w = (rem / G + 31u) & ~31u;
-    return w > (uint32_t)TILE ? (uint32_t)TILE : w < (uint32_t)TMIN ? (uint32_t)TMIN : w;
+    return cur < G * (uint32_t)(TILE / 4) ? (uint32_t)(TILE / 4) : (uint32_t)TILE;
 }
 
 template <int TARGET>
@@ -341,8 +339,10 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint32
             if (st != 0) return;
             uint2 d = make_uint2(0u, 0u);
             const uint32_t cur = *reinterpret_cast<volatile unsigned int*>(&sched[0]);
+            // (Holding the sorter back near the end of the launch, so that no CTA sits on three drawn tiles when the cursor runs
+            // out, halves the spread of the CTAs' finishing times but costs every CTA more than it saves: 60 -> 62 us.)
             if (cur < nblocks) {
-                const uint32_t want = chunk_want<C::TILE, C::TMIN>(cur, nblocks, gridDim.x);
+                const uint32_t want = chunk_want<C::TILE>(cur, gridDim.x);
                 const uint32_t pos = atomicAdd(&sched[0], want);
                 if (pos < nblocks) d = make_uint2(pos, nblocks - pos < want ? nblocks - pos : want);
             }
