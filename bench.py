@@ -490,9 +490,12 @@ def bench_c5_mixed_batch(L, b, torch, dist, rank, world, payload, total_images, 
     nblk = nb * nb
     tex = nblk * 16
     mine = plan_shards([1.0] * total_images, world)[rank]
-    ua = [i for i in mine if i % 2 == 0]
-    es = [i for i in mine if i % 2 == 1]
-    res = {"workload": "%d textures of 2048x2048 (even = UASTC, odd = ETC1S), image i on rank i mod %d: %d per GPU" % (total_images, world, len(mine)),
+    # kinds alternate along every rank's own list (image i = r + G m is UASTC when m + r is even): with "i even" and an even
+    # number of ranks, all UASTC images would land on the even ranks and all ETC1S images on the odd ones
+    is_uastc = lambda i: ((i // world) + (i % world)) % 2 == 0
+    ua = [i for i in mine if is_uastc(i)]
+    es = [i for i in mine if not is_uastc(i)]
+    res = {"workload": "%d textures of 2048x2048, half UASTC half ETC1S (alternating on every rank), image i on rank i mod %d: %d per GPU" % (total_images, world, len(mine)),
            "images_total": total_images, "images_this_rank": len(mine)}
     orc_u = load_oracle()
     cores = max(1, (os.cpu_count() or 1) // world)
@@ -542,8 +545,6 @@ def bench_c5_mixed_batch(L, b, torch, dist, rank, world, payload, total_images, 
                         st = L.b2bu_uastc_transcode(tgt, h_in.data_ptr() + k * nblk * 16, nblk * 16, h_out.data_ptr() + k * nblk * ob, nblk * ob, ctypes.byref(fb))
                     assert st == 0, st
             host_images()
-            if world > 1:
-                dist.barrier()
             t0 = time.perf_counter()
             host_images()
             e2e_u[tgt] = (time.perf_counter() - t0, m)
@@ -672,7 +673,9 @@ def main():
     numa, numa_why = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a mismatched collective must fail in minutes, not after NCCL's default 10-minute watchdog on every rank
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=420))
     L = b.lib()
     assert L.b2bu_init(local_rank) == 0, L.b2bu_last_cuda_error().decode()
 
