@@ -95,6 +95,7 @@ def lib() -> ctypes.CDLL:
     L.b2bu_crc16.restype = c.c_uint16
     L.b2bu_crc16.argtypes = [u8p, sz, c.c_uint16]
     L.b2bu_read_to.argtypes = [c.c_int, u8p, sz, c.c_void_p, c.c_void_p, c.c_uint32, c.POINTER(c.c_uint32), u8p, c.c_uint64, u64p]
+    L.b2bu_read_to_flags.argtypes = L.b2bu_read_to.argtypes + [c.c_uint32]
     _LIB = L
     return L
 
@@ -302,24 +303,32 @@ def read_header(buf) -> Header:
     return Header(**{f: getattr(ch, f) for f in _HEADER_FIELDS})
 
 
-def _read_to(target: int, buf) -> Tuple[Header, List[Image]]:
+def _read_to(target: int, buf, apply_y_flip: bool = False) -> Tuple[Header, List[Image]]:
     L = lib()
     src, n = _buf(buf)
     ch = _CHeader()
     count = ctypes.c_uint32(0)
     need = ctypes.c_uint64(0)
-    _check(L.b2bu_read_to(target, src, n, ctypes.byref(ch), None, 0, ctypes.byref(count), None, 0, ctypes.byref(need)))
+    flags = 1 if apply_y_flip else 0                      # B2BU_READ_APPLY_Y_FLIP
+    _check(L.b2bu_read_to_flags(target, src, n, ctypes.byref(ch), None, 0, ctypes.byref(count), None, 0, ctypes.byref(need), flags))
     imgs = (_CImage * max(count.value, 1))()
     out = (ctypes.c_uint8 * max(need.value, 1))()
-    _check(L.b2bu_read_to(target, src, n, ctypes.byref(ch), imgs, count.value, ctypes.byref(count), out, need.value, ctypes.byref(need)))
+    _check(L.b2bu_read_to_flags(target, src, n, ctypes.byref(ch), imgs, count.value, ctypes.byref(count), out, need.value, ctypes.byref(need), flags))
     raw = memoryview(out)
     images = [Image(im.w, im.h, im.stride, bytes(raw[im.offset:im.offset + im.nbytes])) for im in imgs[:count.value]]
     return Header(**{f: getattr(ch, f) for f in _HEADER_FIELDS}), images
 
 
-def read_to_rgba(buf) -> Tuple[Header, List[Image]]:
-    """basis.rs:8 -- returns (Header, images) like the reference."""
-    return _read_to(RGBA, buf)
+def read_to_rgba(buf, apply_y_flip: bool = False) -> Tuple[Header, List[Image]]:
+    """basis.rs:8 -- returns (Header, images) like the reference.  apply_y_flip (opt-in, not in the reference's signature):
+    honour Header::has_y_flipped the way the reference's own tests do (tests/common.rs:284-301 rgba_rows)."""
+    return _read_to(RGBA, buf, apply_y_flip)
+
+
+def rgba_rows(image: "Image", y_flipped: bool) -> List[bytes]:
+    """tests/common.rs:284-301 of the reference: the first h rows of `stride` bytes, trimmed to w pixels, reversed when flipped"""
+    rows = [bytes(image.data[y * image.stride: y * image.stride + 4 * image.w]) for y in range(image.h)]
+    return rows[::-1] if y_flipped else rows
 
 
 def read_to_etc1(buf) -> List[Image]:

@@ -111,6 +111,46 @@ int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header
     }
 }
 
+int b2bu_read_to_flags(int target, const uint8_t* buf, size_t len, b2bu_header* header, b2bu_image* images, uint32_t max_images,
+                       uint32_t* num_images, uint8_t* out, uint64_t out_cap, uint64_t* out_needed, uint32_t flags)
+{
+    try {
+        b2bu_header h;
+        uint32_t n = 0;
+        std::vector<b2bu_image> local;
+        // the flip needs every image's geometry, whatever the caller's array holds
+        if ((flags & B2BU_READ_APPLY_Y_FLIP) && out && target == B2BU_RGBA) {
+            uint64_t need = 0;
+            int st = read_to_impl(target, buf, len, &h, nullptr, 0, &n, nullptr, 0, &need);
+            if (st) return st;
+            local.resize(n);
+        }
+        int st = read_to_impl(target, buf, len, &h, local.empty() ? images : local.data(), local.empty() ? max_images : (uint32_t)local.size(),
+                              &n, out, out_cap, out_needed);
+        if (header) *header = h;
+        if (num_images) *num_images = n;
+        if (st || local.empty()) return st;
+        for (uint32_t i = 0; i < n && i < max_images && images; i++) images[i] = local[i];
+        if (!(h.flags & 2u)) return B2BU_OK;                                       // HeaderFlags::YFlipped (basis.rs:411-415)
+        std::vector<uint8_t> row;
+        for (const b2bu_image& im : local) {
+            if (im.stride == 0 || (uint64_t)im.h * im.stride > im.nbytes) continue;
+            row.resize(im.stride);
+            uint8_t* base = out + im.offset;
+            for (uint32_t a = 0, b = im.h ? im.h - 1 : 0; a < b; a++, b--) {      // tests/common.rs:284-301: the first h rows, reversed
+                memcpy(row.data(), base + (uint64_t)a * im.stride, im.stride);
+                memcpy(base + (uint64_t)a * im.stride, base + (uint64_t)b * im.stride, im.stride);
+                memcpy(base + (uint64_t)b * im.stride, row.data(), im.stride);
+            }
+        }
+        return B2BU_OK;
+    } catch (const std::bad_alloc&) {
+        return B2BU_ERR_NOMEM;
+    } catch (...) {
+        return B2BU_ERR_ARGUMENT;
+    }
+}
+
 static int read_to_impl(int target, const uint8_t* buf, size_t len, b2bu_header* header, b2bu_image* images, uint32_t max_images,
                         uint32_t* num_images, uint8_t* out, uint64_t out_cap, uint64_t* out_needed)
 {

@@ -203,6 +203,16 @@ int b2bu_crc16_dev(const void* d_data, size_t len, uint16_t crc, uint16_t* resul
 int b2bu_read_to(int target, const uint8_t* buf, size_t len, b2bu_header* header, b2bu_image* images,
                  uint32_t max_images, uint32_t* num_images, uint8_t* out, uint64_t out_cap, uint64_t* out_needed);
 
+/* b2bu_read_to with options.  B2BU_READ_APPLY_Y_FLIP: the reference parses the header's YFlipped flag (Header::has_y_flipped,
+ * basis.rs:467-469) but leaves acting on it to the caller -- its own tests do it in tests/common.rs:284-301 (rgba_rows: the
+ * first `h` rows of `stride` bytes, in reverse order when the flag is set).  With this option and target B2BU_RGBA, images of a
+ * file whose header has the flag come back with their first `h` pixel rows already in that reversed order (rows past `h`, the
+ * padding of the last block row, stay where they are); every other case is b2bu_read_to unchanged. */
+enum b2bu_read_flags { B2BU_READ_APPLY_Y_FLIP = 1 };
+int b2bu_read_to_flags(int target, const uint8_t* buf, size_t len, b2bu_header* header, b2bu_image* images,
+                       uint32_t max_images, uint32_t* num_images, uint8_t* out, uint64_t out_cap, uint64_t* out_needed,
+                       uint32_t flags);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

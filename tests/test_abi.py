@@ -26,6 +26,20 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, n), f"{n} declared in include/b2bu.h but not exported"
 
 
+def test_rust_shim_binds_exactly_the_declared_symbols():
+    """rust/src/ffi.rs is the binding a maintainer of the reference crate would add; it cannot be compiled here
+    (no rustc), so at least its extern block must name exactly the functions include/b2bu.h declares, with as many arguments."""
+    hdr = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "b2bu.h").read_text(), flags=re.S)
+    rs = re.sub(r"//.*", "", (ROOT / "rust" / "src" / "ffi.rs").read_text())
+    c_args = {m.group(1): len([a for a in m.group(2).split(",") if a.strip() and a.strip() != "void"])
+              for m in re.finditer(r"\b(b2bu_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)}
+    rs_args = {m.group(1): len([a for a in m.group(2).split(",") if a.strip()])
+               for m in re.finditer(r"pub fn (b2bu_[a-z0-9_]+)\s*\(([^)]*)\)", rs)}
+    assert set(c_args) == set(declared_symbols())
+    assert set(rs_args) == set(c_args), (sorted(set(c_args) - set(rs_args)), sorted(set(rs_args) - set(c_args)))
+    assert rs_args == c_args
+
+
 def test_host_only_entry_points_work_without_gpu():
     import basisu_rs_b200 as b
     from basis_writer import uastc_file, crc16

@@ -393,3 +393,23 @@ def test_slices_dev_batch_of_equal_textures_is_one_launch(gpu_lib, oracle):
         for k in range(nimg):
             _, _, want = oracle_transcode(oracle, t, blocks[k], nb)
             assert (got[k * nb * nb * ob:(k + 1) * nb * nb * ob] == want).all(), (t, k)
+
+
+def test_y_flip_option_reverses_the_first_h_rows_like_the_reference_tests(gpu_lib, oracle):
+    """Header::has_y_flipped (basis.rs:467-469) is only consumed by the reference's tests (tests/common.rs:284-301 rgba_rows):
+    b2bu_read_to_flags(B2BU_READ_APPLY_Y_FLIP) delivers that row order; without the option, or without the header flag, the
+    image is the reference's."""
+    nbx, nby = 5, 3
+    blk = random_blocks(nbx * nby, seed=31)
+    plain = build_basis([dict(data=blk.tobytes(), orig_width=4 * nbx - 1, orig_height=4 * nby - 2, num_blocks_x=nbx, num_blocks_y=nby)], tex_format=1)
+    flipped = build_basis([dict(data=blk.tobytes(), orig_width=4 * nbx - 1, orig_height=4 * nby - 2, num_blocks_x=nbx, num_blocks_y=nby)], tex_format=1, flags=2)
+    h0, (ref,) = gpu_lib.read_to_rgba(plain)
+    h1, (same,) = gpu_lib.read_to_rgba(flipped)
+    h2, (flip,) = gpu_lib.read_to_rgba(flipped, apply_y_flip=True)
+    h3, (noflag,) = gpu_lib.read_to_rgba(plain, apply_y_flip=True)
+    assert not h0.has_y_flipped() and h1.has_y_flipped() and h2.has_y_flipped()
+    assert same.data == ref.data and noflag.data == ref.data
+    assert (flip.w, flip.h, flip.stride) == (ref.w, ref.h, ref.stride) == (4 * nbx - 1, 4 * nby - 2, 16 * nbx)
+    assert gpu_lib.rgba_rows(flip, False) == gpu_lib.rgba_rows(ref, True)                 # the flipped order, delivered
+    s, hh = ref.stride, ref.h
+    assert flip.data[hh * s:] == ref.data[hh * s:]                                      # padding rows of the last block row stay
