@@ -201,16 +201,12 @@ template <int TARGET> struct PipeCfg {
 
 // Tiles are handed out DYNAMICALLY: the CTAs of a launch draw block ranges from one global cursor (sched[0]).  Equal static
 // shares left the slowest SM 15 % behind the median (identical work, different instruction-fetch and memory latencies), and
-// the launch lasts as long as its slowest CTA.  The first round hands every CTA a short tile (TILE/4) so that the workers start
-// early; after that every tile is a full one.  (Guided self-scheduling -- tiles that shrink towards the end of the launch so
-// that the CTAs finish together -- was measured and lost: a tile's fixed costs, the sort's barriers and the bins' padding to 32
-// blocks, weigh more on small tiles than the imbalance of at most one tile costs.  ASTC: full tiles 58 us, shrinking to a
-// quarter 60, to an eighth 66.)
-template <int TILE>
-__device__ __forceinline__ uint32_t chunk_want(uint32_t cur, uint32_t G)
-{
-    return cur < G * (uint32_t)(TILE / 4) ? (uint32_t)(TILE / 4) : (uint32_t)TILE;
-}
+// the launch lasts as long as its slowest CTA.  Tile 0 of every CTA is a fixed short one (TILE/4 blocks at blockIdx * TILE/4:
+// no round trip to the cursor in front of the first load, and the workers start early); everything behind the first round is
+// drawn from the cursor in full tiles.  (Guided self-scheduling -- tiles that shrink towards the end of the launch so that the
+// CTAs finish together -- was measured and lost: a tile's fixed costs, the sort's barriers and the bins' padding to 32 blocks,
+// weigh more on small tiles than the imbalance of at most one tile costs.  ASTC: full tiles 58 us, shrinking to a quarter 60,
+// to an eighth 66.)
 
 template <int TARGET>
 __global__ void __launch_bounds__(PipeCfg<TARGET>::THREADS, 1)
@@ -338,13 +334,19 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint32
         auto draw = [&](uint32_t j) {
             if (st != 0) return;
             uint2 d = make_uint2(0u, 0u);
-            const uint32_t cur = *reinterpret_cast<volatile unsigned int*>(&sched[0]);
-            // (Holding the sorter back near the end of the launch, so that no CTA sits on three drawn tiles when the cursor runs
-            // out, halves the spread of the CTAs' finishing times but costs every CTA more than it saves: 60 -> 62 us.)
-            if (cur < nblocks) {
-                const uint32_t want = chunk_want<C::TILE>(cur, gridDim.x);
-                const uint32_t pos = atomicAdd(&sched[0], want);
-                if (pos < nblocks) d = make_uint2(pos, nblocks - pos < want ? nblocks - pos : want);
+            constexpr uint32_t T0 = (uint32_t)C::TILE / 4u;
+            const uint32_t round0 = gridDim.x * T0;            // blocks of the fixed first round
+            if (j == 0u) {
+                const uint32_t pos = blockIdx.x * T0;
+                if (pos < nblocks) d = make_uint2(pos, nblocks - pos < T0 ? nblocks - pos : T0);
+            } else if (round0 < nblocks) {
+                const uint32_t cur = *reinterpret_cast<volatile unsigned int*>(&sched[0]);
+                // (Holding the sorter back near the end of the launch, so that no CTA sits on drawn tiles when the cursor runs
+                // out, halves the spread of the CTAs' finishing times but costs every CTA more than it saves: 60 -> 62 us.)
+                if (cur < nblocks - round0) {
+                    const uint32_t pos = round0 + atomicAdd(&sched[0], (uint32_t)C::TILE);
+                    if (pos < nblocks) d = make_uint2(pos, nblocks - pos < (uint32_t)C::TILE ? nblocks - pos : (uint32_t)C::TILE);
+                }
             }
             tdesc[j % C::ND] = d;
             __threadfence_block();

@@ -1,5 +1,8 @@
-for tool in memcheck initcheck racecheck; do
-  echo "== $tool"
-  timeout 500 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_k1_k3.py > gpurun_out/sanitizer_$tool.txt 2>&1
-  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|ok" gpurun_out/sanitizer_$tool.txt | tail -8
+timeout 600 python -m pytest tests/test_gpu_uastc.py tests/test_gpu_witness.py -m gpu -x -q 2>&1 | tail -2
+for lib in libb2bu.so libv_r01.so; do
+B2BU_LIBRARY=$PWD/basisu_rs_b200/$lib timeout 200 python bench.py --all-targets --no-cpu-baseline --steps 200 --e2e-steps 2 --configs none 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('$lib', round(d['ms_per_step']*1e3,1), round(d['ms_per_step_median']*1e3,1), ' '.join('%s=%.0f'%(k,v['us_per_launch']) for k,v in d['extra'].items() if 'random' not in k))
+"
 done
