@@ -1,8 +1,7 @@
-timeout 600 python -m pytest tests/test_gpu_uastc.py tests/test_gpu_witness.py -m gpu -x -q 2>&1 | tail -2
-for lib in libb2bu.so libv_r01.so; do
-B2BU_LIBRARY=$PWD/basisu_rs_b200/$lib timeout 200 python bench.py --all-targets --no-cpu-baseline --steps 200 --e2e-steps 2 --configs none 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('$lib', round(d['ms_per_step']*1e3,1), round(d['ms_per_step_median']*1e3,1), ' '.join('%s=%.0f'%(k,v['us_per_launch']) for k,v in d['extra'].items() if 'random' not in k))
-"
-done
+for t in astc rgba bc7 etc1 etc2; do bash tools/gpu_profile.sh $t > /dev/null 2>&1; done
+bash tools/gpu_profile_etc1s.sh > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_default.csv python bench.py --steps 2 --warmup 1 --c5-images 32 --c4-slices 16 > gpurun_out/bench_under_ncu.log 2>&1
+python tools/trace_pipeline.py astc > gpurun_out/trace_astc.txt 2>&1
+python tools/trace_pipeline.py rgba > gpurun_out/trace_rgba.txt 2>&1
+python bench.py --all-targets --steps 200 > gpurun_out/bench_all_targets.json 2> gpurun_out/bench_all_targets.err
+ls -la gpurun_out/*.ncu-rep gpurun_out/launches_default.csv
