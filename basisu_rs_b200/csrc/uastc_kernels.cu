@@ -471,10 +471,13 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint32
                 item = __shfl_sync(0xFFFFFFFFu, item, 0);
             }
             if (item >= nitems) break;
+            // descriptor and block index are loaded side by side (the index of a padding lane is stale, never used): under
+            // load a shared-memory access costs ~200 cycles, and an item's descriptor -> index -> block chain is latency
+            // nothing else in the warp can hide
             const uint32_t desc = itm[item];
+            const uint32_t idx = ord[item * 32 + lane];
             const uint32_t mode = desc & 0xFFu;
             if ((uint32_t)lane < (desc >> 8)) {
-                const uint32_t idx = ord[item * 32 + lane];
                 const uint4 b = tin[idx];
                 BlockOut o_;
                 TileRowSink sink{tin + idx, reinterpret_cast<uint4*>(tout) + idx, (uint64_t)C::TILE};
