@@ -1106,22 +1106,25 @@ B2BU_DI uint2 etc1_block(const uint32_t (&px)[16], const EtcFlags& f, const DevT
     for (int k = 0; k < 3; k++) { thr_tr[k] = flip ? thr[0][k] : thr[1][k]; thr_bl[k] = flip ? thr[1][k] : thr[0][k]; }
 
     // selector s = #(lum >= t_k); its ETC1 code [3,2,0,1] (etc.rs:433) has msb = (s < 2) = (lum < t1) and
-    // lsb = (s == 0 || s == 3) = (lum < t0) || (lum >= t2): three compares and two conditional ORs per texel
-    uint32_t selbits = 0;
+    // lsb = (s == 0 || s == 3) = (lum < t0) || (lum >= t2).  Both are SIGN bits -- of lum - t1, and of (lum - t0) | ~(lum - t2)
+    // (all operands are below 2^18) -- and a funnel shift (acc : x) << 1 appends the sign of x to acc in one instruction: the
+    // texels are visited in descending bit position, so the two 16-bit planes come out in ETC1's order without any
+    // per-texel insert (3 subtractions, which the fma pipe takes, + 1 LOP3 + 2 SHF instead of 3 compares + 4 predicated ORs).
+    uint32_t msb = 0u, lsb = 0u;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const int x = i & 3, y = i >> 2;
+    for (int bitpos = 15; bitpos >= 0; bitpos--) {
+        const int pid = bitpos >= 8 ? bitpos - 8 : bitpos + 8;        // byte 1 holds pixels 0..7, byte 0 pixels 8..15
+        const int x = pid >> 2, y = pid & 3, i = y * 4 + x;           // ETC pixel id = x * 4 + y (etc.rs:363-393)
         const int qx = x >> 1, qy = y >> 1;
         const int t0 = (qx == qy) ? thr[qx][0] : (qx ? thr_tr[0] : thr_bl[0]);
         const int t1 = (qx == qy) ? thr[qx][1] : (qx ? thr_tr[1] : thr_bl[1]);
         const int t2 = (qx == qy) ? thr[qx][2] : (qx ? thr_tr[2] : thr_bl[2]);
         // 108 R + 366 G + 38 B as two byte dot products (366 = 2 x 183 does not fit a signed byte weight)
         const int lum = __dp4a(px[i], 0x0026B76Cu, __dp4a(px[i], 0x0000B700u, 0u));
-        const int pid = x * 4 + y;
-        const int bitpos = pid < 8 ? 8 + pid : pid - 8;  // byte 1 holds pixels 0..7, byte 0 pixels 8..15
-        if (lum < t1) selbits |= 1u << bitpos;
-        if (lum < t0 || lum >= t2) selbits |= 1u << (16 + bitpos);
+        msb = __funnelshift_l((uint32_t)(lum - t1), msb, 1);
+        lsb = __funnelshift_l((uint32_t)(lum - t0) | ~(uint32_t)(lum - t2), lsb, 1);
     }
+    const uint32_t selbits = (msb & 0xFFFFu) | (lsb << 16);
     return make_uint2(hdr, selbits);
 }
 
