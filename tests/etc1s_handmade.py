@@ -119,6 +119,77 @@ def build():
                 expect_ep=expect_ep, expect_sel=expect_sel, ep_cb=ep_cb, sel_cb=sel_cb)
 
 
+def build_runs():
+    """A second hand-made body for the paths the first one does not touch: a GRAYSCALE endpoint codebook, a HUFFMAN-coded
+    (XOR-DPCM) selector codebook, the predictor repeat symbol (256 + 4-bit-chunk VLC), the selector-history run symbol with a
+    plain count and with the 63 escape + 7-bit-chunk VLC, and a history hit that swaps two different entries."""
+    n, hist = 4, 4
+    # ---------------- endpoint codebook, grayscale: only R is coded, G and B copy it
+    w = Bits()
+    col = [huff_table(w, 32, {1: 1, 31: 1}) for _ in range(3)]        # '0' -> +1, '1' -> -1
+    inten = huff_table(w, 8, {0: 1, 3: 1})                            # '0' -> +0, '1' -> +3
+    w.put(1, 1)                                                       # grayscale
+    w.code(inten[3]).code(col[1][1])                                  # entry 0: inten 3, grey 17
+    w.code(inten[3]).code(col[1][1])                                  # entry 1: inten 6, grey 18
+    w.code(inten[0]).code(col[1][31])                                 # entry 2: inten 6, grey 17
+    w.code(inten[3]).code(col[1][31])                                 # entry 3: inten (6 + 3) & 7 = 1, grey 16
+    endpoints = w.bytes()
+    ep_cb = [(3, 17, 17, 17), (6, 18, 18, 18), (6, 17, 17, 17), (1, 16, 16, 16)]
+
+    # ---------------- selector codebook, Huffman coded: global = 0, hybrid = 0, raw = 0, the delta model, selector 0 as four raw
+    # bytes, then four symbols per selector, each XOR-ed onto the same row of the previous selector
+    w = Bits()
+    w.put(0, 1).put(0, 1).put(0, 1)
+    dsel = huff_table(w, 256, {0x00: 1, 0xFF: 1})                     # '0' -> row unchanged, '1' -> row inverted
+    for r in (0x1B, 0x1B, 0xE4, 0xE4):
+        w.put(r, 8)
+    w.code(dsel[0x00]).code(dsel[0xFF]).code(dsel[0x00]).code(dsel[0xFF])   # selector 1: 1B E4 E4 1B
+    w.code(dsel[0xFF]).code(dsel[0xFF]).code(dsel[0xFF]).code(dsel[0xFF])   # selector 2: E4 1B 1B E4
+    w.code(dsel[0x00]).code(dsel[0x00]).code(dsel[0x00]).code(dsel[0x00])   # selector 3: the same rows
+    selectors = w.bytes()
+    sel_cb = [[0x1B, 0x1B, 0xE4, 0xE4], [0x1B, 0xE4, 0xE4, 0x1B], [0xE4, 0x1B, 0x1B, 0xE4], [0xE4, 0x1B, 0x1B, 0xE4]]
+
+    # ---------------- slice models
+    w = Bits()
+    pred = huff_table(w, 257, {83: 1, 256: 1})         # '0' -> 83 = 3|0<<2|1<<4|1<<6 (delta, left / up, up), '1' -> 256 = repeat
+    delta = huff_table(w, 4, {0: 2, 1: 2, 2: 2, 3: 2})                # '00' +0, '01' +1, '10' +2, '11' +3 (mod 4 endpoints)
+    sel = huff_table(w, n + hist + 1, {1: 2, 2: 2, 7: 2, 8: 2})       # '00' selector 1, '01' selector 2, '10' history[3], '11' = n + hist: run
+    rle = huff_table(w, 64, {0: 1, 63: 1})                            # '0' -> count 0, '1' -> 63 = escape, a 7-bit-chunk VLC follows
+    w.put(hist, 13)
+    tables = w.bytes()
+
+    # ---------------- the slice: 8 x 2 blocks.  history = [0,0,0,0], insert position 2 (wraps back to 2 after 3)
+    w = Bits()
+    # (0,0): predictor symbol 83 for the 2x2 group; delta +1 -> endpoint 1; selector 1 -> history [0,0,1,0]
+    w.code(pred[83]).code(delta[1]).code(sel[1])
+    # (1,0): left -> 1; selector 2 -> history [0,0,1,2]
+    w.code(sel[2])
+    # (2,0): predictor symbol 256 = repeat the previous symbol; VLC(4) value 0 (one 5-bit chunk, no continuation) -> this group and
+    #        2 more use 83.  delta +3: 1 + 3 = 4 -> wraps to 0; history[3] = 2, swapped with history[1] -> [0,2,1,0]
+    w.code(pred[256]).put(0, 5).code(delta[3]).code(sel[7])
+    # (3,0): left -> 0; run symbol, count symbol 0 -> this block and 3 + 0 - 1 = 2 more read history[0] = 0
+    w.code(sel[8]).code(rle[0])
+    # (4,0): (repeat 2 -> 1) delta +2 -> 2; selector from the run
+    w.code(delta[2])
+    # (5,0): left -> 2; run ends here
+    # (6,0): (repeat 1 -> 0) delta +0 -> 2; selector 1 -> history [0,2,1,0] (insert position 2 -> 3)
+    w.code(delta[0]).code(sel[1])
+    # (7,0): left -> 2; run symbol with the escape: count symbol 63, then VLC(7) value 1 (one 8-bit chunk) -> 3 + 1 - 1 = 3 more blocks
+    w.code(sel[8]).code(rle[63]).put(1, 8)
+    # row 1: every predictor is "up" (upper nibble of 83), no predictor or delta symbols
+    # (0,1) (1,1) (2,1): the run -> history[0] = 0
+    # (3,1): selector 2 -> inserted at position 3: history [0,2,1,2], insert position wraps to 2
+    w.code(sel[2])
+    # (4,1): history[3] = 2, swapped with history[1] = 2
+    w.code(sel[7])
+    # (5,1): selector 1   (6,1): selector 2   (7,1): selector 1
+    w.code(sel[1]).code(sel[2]).code(sel[1])
+    expect_ep = np.array([[1, 1, 0, 0, 2, 2, 2, 2], [1, 1, 0, 0, 2, 2, 2, 2]], dtype=np.uint16)
+    expect_sel = np.array([[1, 2, 2, 0, 0, 0, 1, 0], [0, 0, 0, 2, 2, 1, 2, 1]], dtype=np.uint16)
+    return dict(endpoints=endpoints, selectors=selectors, tables=tables, slice=w.bytes(), nbx=8, nby=2, n=n,
+                expect_ep=expect_ep, expect_sel=expect_sel, ep_cb=ep_cb, sel_cb=sel_cb)
+
+
 # ETC1 intensity modifier table (ETC1 specification), ordered as the ETC1S selector value indexes it: -large, -small, +small, +large
 ETC1_MOD = [(8, 2), (17, 5), (29, 9), (42, 13), (60, 18), (80, 24), (106, 33), (183, 47)]
 
@@ -139,9 +210,14 @@ def expected_rgba(case):
                     m = mod[(rows[y] >> (2 * x)) & 3]
                     px = [min(255, max(0, ((c << 3) | (c >> 2)) + m)) for c in (r5, g5, b5)]
                     img[4 * by + y, 4 * bx + x] = px + [255]
-    # two texels worked out by hand as literals: block (2,0) has endpoint 0 = intensity 3, (17,15,17) -> (140,123,140) and selector 1
-    # (texel x has value x): x = 0 -> -42 -> (98, 81, 98); x = 3 -> +42 -> (182, 165, 182)
-    assert tuple(img[0, 8]) == (98, 81, 98, 255) and tuple(img[0, 11]) == (182, 165, 182, 255)
-    # block (3,1): endpoint 1 = intensity 3, (18,16,16) -> (148,132,132), selector 1: x = 1 -> -13 -> (135, 119, 119)
-    assert tuple(img[4, 13]) == (135, 119, 119, 255)
+    if case["nbx"] == 4:
+        # two texels worked out by hand as literals: block (2,0) has endpoint 0 = intensity 3, (17,15,17) -> (140,123,140) and
+        # selector 1 (texel x has value x): x = 0 -> -42 -> (98, 81, 98); x = 3 -> +42 -> (182, 165, 182)
+        assert tuple(img[0, 8]) == (98, 81, 98, 255) and tuple(img[0, 11]) == (182, 165, 182, 255)
+        # block (3,1): endpoint 1 = intensity 3, (18,16,16) -> (148,132,132), selector 1: x = 1 -> -13 -> (135, 119, 119)
+        assert tuple(img[4, 13]) == (135, 119, 119, 255)
+    else:
+        # build_runs(): block (0,0) has endpoint 1 = intensity 6, grey 18 -> 148, selector 1 row 0 = 0x1B (texel x has value 3 - x):
+        # x = 0 -> +106 -> 254; x = 3 -> -106 -> 42
+        assert tuple(img[0, 0]) == (254, 254, 254, 255) and tuple(img[0, 3]) == (42, 42, 42, 255)
     return img

@@ -71,10 +71,11 @@ def test_etc1s_etc1_output_decodes_to_the_rgba_output(gpu_lib, spec, oracle, sha
     dec.close()
 
 
-def test_hand_assembled_etc1s_stream_on_the_gpu(gpu_lib, spec):
-    """the bit-by-bit hand-made stream of tests/etc1s_handmade.py through b2bu_etc1s_open / K2 / K3: hand-derived texels"""
+@pytest.mark.parametrize("which", ["build", "build_runs"])
+def test_hand_assembled_etc1s_stream_on_the_gpu(gpu_lib, spec, which):
+    """the bit-by-bit hand-made streams of tests/etc1s_handmade.py through b2bu_etc1s_open / K2 / K3: hand-derived texels"""
     import etc1s_handmade as hm
-    case = hm.build()
+    case = getattr(hm, which)()
     want = hm.expected_rgba(case)
     dec = gpu_lib.Etc1sDecoder(case["n"], case["n"], case["endpoints"], case["selectors"], case["tables"])
     nbx, nby = case["nbx"], case["nby"]

@@ -79,11 +79,14 @@ def test_oracle_etc1s_etc1_decodes_to_its_rgba(spec, oracle, shape):
     eo.orc_etc1s_close(h)
 
 
-def test_hand_assembled_etc1s_stream_decodes_to_the_hand_derived_result(spec, oracle):
-    """tests/etc1s_handmade.py builds an ETC1S body bit by bit from the published format description (no encoder of ours involved)
-    with the expected indices and texels worked out in its comments: pins the ETC1S oracle on something we did not generate."""
+@pytest.mark.parametrize("which", ["build", "build_runs"])
+def test_hand_assembled_etc1s_stream_decodes_to_the_hand_derived_result(spec, oracle, which):
+    """tests/etc1s_handmade.py builds ETC1S bodies bit by bit from the published format description (no encoder of ours involved)
+    with the expected indices and texels worked out in its comments: pins the ETC1S oracle on something we did not generate.
+    build(): colour codebook, raw selectors, predictors, delta wrap, history insert / hit.  build_runs(): grayscale codebook,
+    Huffman-coded selectors, predictor repeat + VLC, selector runs (plain count and escape + VLC), a swapping history hit."""
     import etc1s_handmade as hm
-    case = hm.build()
+    case = getattr(hm, which)()
     eo = ec.bind(oracle)
     enc = dict(endpoints=case["endpoints"], selectors=case["selectors"], tables=case["tables"])
     e, h = ec.oracle_open(eo, enc, case["n"], case["n"])
