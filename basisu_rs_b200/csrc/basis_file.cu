@@ -154,6 +154,7 @@ int b2bu_read_to_flags(int target, const uint8_t* buf, size_t len, b2bu_header* 
 static int read_to_impl(int target, const uint8_t* buf, size_t len, b2bu_header* header, b2bu_image* images, uint32_t max_images,
                         uint32_t* num_images, uint8_t* out, uint64_t out_cap, uint64_t* out_needed)
 {
+    NvtxScope nv(out ? "b2bu_read_to (upload | CRC-16 | transcode | download)" : "b2bu_read_to (sizing)");
     if (num_images) *num_images = 0;
     if (out_needed) *out_needed = 0;
     if (target < B2BU_RGBA || target > B2BU_UASTC) return B2BU_ERR_ARGUMENT;

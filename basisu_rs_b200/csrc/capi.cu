@@ -85,6 +85,7 @@ int decode_status_word(unsigned long long w, uint64_t* first_bad)
 // the H2D copy of chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap.
 static int uastc_host_run(int target, const uint8_t* blocks, size_t nblocks, size_t bpr, uint8_t* out, uint64_t* first_bad)
 {
+    NvtxScope nv("b2bu K1 host pipeline (H2D | uastc_sorted_kernel | D2H)");
     DeviceCtx* c;
     int st = get_ctx(&c);
     if (st) return st;

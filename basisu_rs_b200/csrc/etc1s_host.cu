@@ -288,7 +288,7 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
     P.l1_ofs[4] = h->l1_ofs[set][4];
     P.num_endpoints = h->num_endpoints; P.num_selectors = h->num_selectors; P.hist_size = h->hist_size; P.is_video = h->is_video ? 1u : 0u;
     P.status = static_cast<uint32_t*>(h->d_status);
-    CK(launch_etc1s_decode(P, dplan, s));
+    { NvtxScope nv("b2bu K2 etc1s_entropy_decode"); CK(launch_etc1s_decode(P, dplan, s)); }
     count_launch(1);
     CK(cudaEventRecord(h->ev[1], s));
 
@@ -302,6 +302,7 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
     for (size_t i = 0; i < ns; i++) if (status[i]) return (int)status[i];          // first failing slice in file order
 
     const uint32_t* idx = static_cast<const uint32_t*>(h->d_idx);
+    NvtxScope nv3("b2bu K3 etc1s gather + D2H");
     if (target == B2BU_ETC1) {
         // images are the slices in order and ETC1 output does not depend on the slice shape: one gather over everything
         CK(launch_etc1s_gather_etc1(idx, blocks_total, h->d_endpoints, h->d_sel_etc1, h->d_out, c->sm_count, s));

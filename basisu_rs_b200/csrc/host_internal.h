@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <mutex>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>          // header-only: the ranges cost nothing unless a tool (nsys, ncu --nvtx) is attached
 #include "../../include/b2bu.h"
 
 namespace b2bu {
@@ -39,6 +40,14 @@ struct DeviceCtx {
 
 // basis.rs:520-535
 struct SliceDesc { uint32_t image_index, level_index, flags, orig_width, orig_height, num_blocks_x, num_blocks_y, file_ofs, file_size, crc; };
+
+// NVTX range around a stage of the host runtime (ranges around K1 / K2 / K3 and the copies)
+struct NvtxScope {
+    explicit NvtxScope(const char* name) { nvtxRangePushA(name); }
+    ~NvtxScope() { nvtxRangePop(); }
+    NvtxScope(const NvtxScope&) = delete;
+    NvtxScope& operator=(const NvtxScope&) = delete;
+};
 
 int get_ctx(DeviceCtx** out);
 int ensure(void** p, size_t* cap, size_t need);
