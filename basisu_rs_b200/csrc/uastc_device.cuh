@@ -382,8 +382,11 @@ B2BU_DI void mad4_if(uint32_t (&r)[4], uint32_t on, const uint32_t (&d)[4], uint
 #endif
 }
 
-// One row of four texels.  NSUB: subsets (1..3); DUAL: two weight planes (one subset).
-template <int NSUB, bool DUAL>
+// One row of four texels.  NSUB: subsets (1..3); DUAL: two weight planes (one subset); ALPHA = false: the caller never looks at
+// byte 3 of a texel (UASTC -> ETC1), so the alpha multiply-add and its byte permute are left out (byte 3 = 0).
+// (Extracting the weight byte with a byte dot product -- IDP.4A issues on the fma pipe, tools/probe_pipes.cu -- instead of a byte
+// permute was measured: RGBA 94 -> 97 us, so the permute stays.)
+template <int NSUB, bool DUAL, bool ALPHA>
 B2BU_DI uint4 interp_row(const Canon& c, uint32_t wr0, uint32_t wr1, uint32_t pwr)
 {
     uint32_t px[4];
@@ -402,7 +405,8 @@ B2BU_DI uint4 interp_row(const Canon& c, uint32_t wr0, uint32_t wr1, uint32_t pw
         if (NSUB >= 2) mad4_if(r, pwr & (1u << (2 * x)), c.d[1], w, c.l[1]);
         if (NSUB == 3) mad4_if(r, pwr & (2u << (2 * x)), c.d[2], w, c.l[2]);
         // byte 2 of every channel word -> R, G, B, A
-        px[x] = __byte_perm(__byte_perm(r[0], r[1], 0x0062), __byte_perm(r[2], r[3], 0x0062), 0x5410);
+        if (ALPHA) px[x] = __byte_perm(__byte_perm(r[0], r[1], 0x0062), __byte_perm(r[2], r[3], 0x0062), 0x5410);
+        else px[x] = __byte_perm(__byte_perm(r[0], r[1], 0x3362), r[2], 0x7610);       // byte 3 of a channel word is zero
     }
     return make_uint4(px[0], px[1], px[2], px[3]);
 }
@@ -431,21 +435,21 @@ struct TileRowSink {
     B2BU_DI void row(int y, const uint4& v) { if (y == 0) *row0 = v; else rows123[(uint64_t)(y - 1) * stride] = v; }
 };
 
-template <int NSUB, bool DUAL, class Sink> B2BU_DI void interp_rows(Canon& c, Sink& sink)
+template <int NSUB, bool DUAL, bool ALPHA, class Sink> B2BU_DI void interp_rows(Canon& c, Sink& sink)
 {
     if (Sink::ROLLED) {
 #pragma unroll 1
         for (int y = 0; y < 4; y++) {
-            sink.row(y, interp_row<NSUB, DUAL>(c, c.w0.x, c.w1.x, c.pw));
+            sink.row(y, interp_row<NSUB, DUAL, ALPHA>(c, c.w0.x, c.w1.x, c.pw));
             c.w0.x = c.w0.y; c.w0.y = c.w0.z; c.w0.z = c.w0.w;
             if (DUAL) { c.w1.x = c.w1.y; c.w1.y = c.w1.z; c.w1.z = c.w1.w; }
             c.pw >>= 8;
         }
     } else {
-        sink.row(0, interp_row<NSUB, DUAL>(c, c.w0.x, c.w1.x, c.pw));
-        sink.row(1, interp_row<NSUB, DUAL>(c, c.w0.y, c.w1.y, c.pw >> 8));
-        sink.row(2, interp_row<NSUB, DUAL>(c, c.w0.z, c.w1.z, c.pw >> 16));
-        sink.row(3, interp_row<NSUB, DUAL>(c, c.w0.w, c.w1.w, c.pw >> 24));
+        sink.row(0, interp_row<NSUB, DUAL, ALPHA>(c, c.w0.x, c.w1.x, c.pw));
+        sink.row(1, interp_row<NSUB, DUAL, ALPHA>(c, c.w0.y, c.w1.y, c.pw >> 8));
+        sink.row(2, interp_row<NSUB, DUAL, ALPHA>(c, c.w0.z, c.w1.z, c.pw >> 16));
+        sink.row(3, interp_row<NSUB, DUAL, ALPHA>(c, c.w0.w, c.w1.w, c.pw >> 24));
     }
 }
 
@@ -476,12 +480,12 @@ B2BU_DI uint32_t compress4to2(uint32_t x)
 constexpr uint32_t kTwoSubsetModes = (1u << 2) | (1u << 4) | (1u << 7) | (1u << 9) | (1u << 16);
 constexpr uint32_t kDualPlaneModes = (1u << 6) | (1u << 11) | (1u << 13) | (1u << 17);
 
-template <class Sink> B2BU_DI void interp_block(uint32_t mode, Canon& c, Sink& sink)
+template <bool ALPHA, class Sink> B2BU_DI void interp_block(uint32_t mode, Canon& c, Sink& sink)
 {
-    if ((kDualPlaneModes >> mode) & 1u) interp_rows<1, true>(c, sink);
-    else if (mode == 3u) interp_rows<3, false>(c, sink);
-    else if ((kTwoSubsetModes >> mode) & 1u) interp_rows<2, false>(c, sink);
-    else interp_rows<1, false>(c, sink);
+    if ((kDualPlaneModes >> mode) & 1u) interp_rows<1, true, ALPHA>(c, sink);
+    else if (mode == 3u) interp_rows<3, false, ALPHA>(c, sink);
+    else if ((kTwoSubsetModes >> mode) & 1u) interp_rows<2, false, ALPHA>(c, sink);
+    else interp_rows<1, false, ALPHA>(c, sink);
 }
 
 // void-extent colour (uastc.rs:387-394): bits 5..36
@@ -1041,21 +1045,24 @@ B2BU_DI uint32_t etc1_apply_bias(uint32_t v0, uint32_t bw, int c, uint32_t limit
 B2BU_DI uint2 etc1_block(const uint32_t (&px)[16], const EtcFlags& f, const DevTables& T)
 {
     // quadrant sums in 16-bit lanes: q[qy][qx]
-    uint32_t srb[2][2] = {{0u, 0u}, {0u, 0u}}, sg[2][2] = {{0u, 0u}, {0u, 0u}};
+    // quadrant sums per channel, q[qy][qx][c], as byte dot products (one IDP.4A on the fma pipe per channel and texel)
+    uint32_t q[2][2][3] = {{{0u, 0u, 0u}, {0u, 0u, 0u}}, {{0u, 0u, 0u}, {0u, 0u, 0u}}};
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const int x = i & 3, y = i >> 2;
-        srb[y >> 1][x >> 1] += px[i] & 0x00FF00FFu;
-        sg[y >> 1][x >> 1] = __dp4a(px[i], 0x00000100u, sg[y >> 1][x >> 1]);       // += G
+#pragma unroll
+        for (int c = 0; c < 3; c++) q[y >> 1][x >> 1][c] = __dp4a(px[i], 1u << (8 * c), q[y >> 1][x >> 1][c]);
     }
     const bool flip = f.flip != 0u;
-    // sub-block 0 = TL + (flip ? TR : BL), sub-block 1 = BR + (flip ? BL : TR)
-    const uint32_t rb0 = srb[0][0] + (flip ? srb[0][1] : srb[1][0]), g0 = sg[0][0] + (flip ? sg[0][1] : sg[1][0]);
-    const uint32_t rb1 = srb[1][1] + (flip ? srb[1][0] : srb[0][1]), g1 = sg[1][1] + (flip ? sg[1][0] : sg[0][1]);
     const uint32_t limit = f.diff ? 31u : 15u;
     uint32_t c0[3], c1[3];
-    c0[0] = ((rb0 & 0xFFFFu) * limit + 1020u) / 2040u; c0[1] = (g0 * limit + 1020u) / 2040u; c0[2] = ((rb0 >> 16) * limit + 1020u) / 2040u;
-    c1[0] = ((rb1 & 0xFFFFu) * limit + 1020u) / 2040u; c1[1] = (g1 * limit + 1020u) / 2040u; c1[2] = ((rb1 >> 16) * limit + 1020u) / 2040u;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        // sub-block 0 = TL + (flip ? TR : BL), sub-block 1 = BR + (flip ? BL : TR)
+        const uint32_t s0 = q[0][0][c] + (flip ? q[0][1][c] : q[1][0][c]), s1 = q[1][1][c] + (flip ? q[1][0][c] : q[0][1][c]);
+        c0[c] = (s0 * limit + 1020u) / 2040u;
+        c1[c] = (s1 * limit + 1020u) / 2040u;
+    }
     if (f.has_bias) {
         const uint32_t bw = kEtc1BiasLut[f.bias & 31u];
 #pragma unroll
@@ -1205,10 +1212,10 @@ B2BU_DI uint32_t transcode_mode_sink(uint32_t mode, const uint4& b, const DevTab
     default: return ERR_MODE;
     }
     if (TARGET == TGT_RGBA) {
-        interp_block(mode, c, sink);
+        interp_block<true>(mode, c, sink);
     } else {
         PxArraySink ps{o.px};
-        interp_block(mode, c, ps);
+        interp_block<TARGET == TGT_ETC2>(mode, c, ps);                 // ETC1 never reads alpha
         o.etc = etc1_block(o.px, f, T);
         if (TARGET == TGT_ETC2) { const uint2 a = etc2_alpha_block(o.px, f.etc2tm, T); o.v = make_uint4(a.x, a.y, o.etc.x, o.etc.y); }
     }

@@ -7,11 +7,11 @@
 #include <cuda_runtime.h>
 
 enum { K_LOP3, K_SHF, K_PRMT, K_IMAD, K_IMADHI, K_IMADWIDE, K_DP4A, K_SEL, K_IADD3, K_SHL, K_SHR, K_LOP_IMAD, K_PRMT_IMAD, K_2ALU_1IMAD,
-       K_1ALU_2IMAD, K_LOP_IMADHI, K_FFMA, K_LOP_FFMA, K_LOP_IMAD_FFMA, K_BFE, K_POPC, K_BREV, K_SHF_IMAD, K_COUNT };
+       K_1ALU_2IMAD, K_LOP_IMADHI, K_FFMA, K_LOP_FFMA, K_LOP_IMAD_FFMA, K_BFE, K_POPC, K_BREV, K_SHF_IMAD, K_LOP_DP4A, K_IMAD_DP4A, K_COUNT };
 static const char* kNames[K_COUNT] = {"lop3", "shf.l.wrap", "prmt", "mad.lo", "mad.hi", "mad.wide", "dp4a", "selp", "add3", "shl", "shr", "lop3+mad.lo",
                                       "prmt+mad.lo", "2 lop3+mad.lo", "lop3+2 mad.lo", "lop3+mad.hi", "ffma", "lop3+ffma", "lop3+mad.lo+ffma", "bfe", "popc", "brev",
-                                      "shf+mad.lo"};
-static const int kOpsPerStep[K_COUNT] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 3, 3, 2, 1, 2, 3, 1, 1, 1, 2};
+                                      "shf+mad.lo", "lop3+dp4a", "mad.lo+dp4a"};
+static const int kOpsPerStep[K_COUNT] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 3, 3, 2, 1, 2, 3, 1, 1, 1, 2, 2, 2};
 
 #define LOP3(x, y, z) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(y), "r"(z))
 #define IMAD(x, y, z) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(z))
@@ -54,6 +54,8 @@ template <int KIND> __global__ void __launch_bounds__(1024) probe(uint32_t* out,
                 if (KIND == K_BFE) asm volatile("bfe.u32 %0, %0, 5, 9;" : "+r"(a[i]));
                 if (KIND == K_POPC) asm volatile("popc.b32 %0, %0;" : "+r"(a[i]));
                 if (KIND == K_BREV) asm volatile("brev.b32 %0, %0;" : "+r"(a[i]));
+                if (KIND == K_LOP_DP4A) { LOP3(a[i], k1, k2); asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(k1), "r"(k2)); }
+                if (KIND == K_IMAD_DP4A) { IMAD(a[i], k1, k2); asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(k1), "r"(k2)); }
                 if (KIND == K_SHF_IMAD) { asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(a[i]) : "r"(k1)); IMAD(a[i], k1, k2); }
             }
         }
