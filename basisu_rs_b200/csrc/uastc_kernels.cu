@@ -231,6 +231,11 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint32
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    // Programmatic dependent launch: the NEXT kernel of the stream may be scheduled onto an SM as soon as this launch's CTA has
+    // left it, and runs its prologue (constant tables -> shared memory, barrier initialisation: nothing an earlier kernel writes)
+    // while the slowest CTAs of this launch are still working; griddepcontrol.wait below holds it back until this launch -- and
+    // everything before it in the stream -- has completed and flushed, so stream order is what it always was.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) *desc_seq = 0u;
     if (tid == 0) {
         for (int i = 0; i < C::NS; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_done[i], C::WORK_WARPS); }
@@ -238,6 +243,7 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint32
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     load_tables(&T, TableBytes<TARGET>::value);  // ends with __syncthreads()
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid == 0) TRACE(60);
 #ifdef B2BU_TRACE
     if (tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_trace[blockIdx.x][57] = gt; }
@@ -558,9 +564,18 @@ static cudaError_t launch_sorted(const uint4* in, void* d_out, uint64_t nblocks,
         const uint64_t want = (n + C::TILE / 4 - 1) / (C::TILE / 4);
         const unsigned grid = (unsigned)(want < (uint64_t)sm_count ? want : (uint64_t)sm_count);
         const size_t ob = (size_t)C::OB;
-        uastc_sorted_kernel<TARGET><<<grid, C::THREADS, C::SMEM, stream>>>(in + done, static_cast<unsigned char*>(d_out) + done * ob, (uint32_t)n, bpr,
-                                                                           index_base + done, d_err, slot);
-        e = cudaGetLastError();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(C::THREADS);
+        cfg.dynamicSmemBytes = C::SMEM;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // see griddepcontrol.* in the kernel
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, uastc_sorted_kernel<TARGET>, in + done, static_cast<void*>(static_cast<unsigned char*>(d_out) + done * ob),
+                               (uint32_t)n, bpr, (uint64_t)(index_base + done), d_err, slot);
         if (e != cudaSuccess) return e;
         done += n;
     }

@@ -1,8 +1,8 @@
-timeout 300 python -m pytest tests/test_gpu_uastc.py -m gpu -x -q 2>&1 | tail -2
-for lib in libb2bu.so libv_base.so libb2bu.so libv_base.so; do
-B2BU_LIBRARY=$PWD/basisu_rs_b200/$lib timeout 200 python bench.py --all-targets --no-cpu-baseline --steps 200 --e2e-steps 2 --configs none 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('$lib', round(d['ms_per_step']*1e3,1), round(d['ms_per_step_median']*1e3,1), ' '.join('%s=%.0f'%(k,v['us_per_launch']) for k,v in d['extra'].items() if 'shuffled' in k))
-"
-done
+python bench.py --gpus 1 --steps 20 --warmup 5 --configs none > gpurun_out/b1.json 2>/dev/null
+python bench.py --gpus 1 --steps 200 --warmup 5 --configs none --all-targets > gpurun_out/b2.json 2>/dev/null
+python - <<'PY'
+import json
+for f in ("b1","b2"):
+    d=json.loads(open("gpurun_out/%s.json"%f).read().strip().splitlines()[-1])
+    print(f, "ms", round(d["ms_per_step"]*1e3,2), "median(separated)", round(d["ms_per_step_median"]*1e3,2), d["timing"]["per_step_us_min"], d["timing"]["per_step_us_max"], "frac", round(d["roofline"]["frac"],3), round(d["per_path_roofline"]["frac_of_per_path_roofline"],3), {k.split("/")[0]:round(v["us_per_launch"],1) for k,v in d.get("extra",{}).items() if "shuffled" in k})
+PY
