@@ -133,15 +133,22 @@ constexpr int kBins = 20;                       // modes 0..18 + the invalid cod
 __constant__ uint8_t kBinOrder[32] = {3, 9, 16, 4, 7, 2, 12, 10, 11, 13, 14, 6, 0, 18, 5, 1, 17, 15, 8, 19,
                                        31, 31, 31, 31, 31, 31, 31, 31, 31, 31, 31, 31};
 
-// tile sizes in blocks (tuned on B200; RGBA stages 48 B per block and slot beside the 16 B of input)
+// tile sizes in blocks, each the best of a 2560..4096 scan on B200 (profiles/tile_scan_r02.txt; the spread over that
+// range is 2..6 %).  RGBA stages 48 B and ETC1 8 B of output per block and slot beside the 16 B of input.
 #ifndef B2BU_TILE16
-#define B2BU_TILE16 4096
+#define B2BU_TILE16 4096        // ETC2, and BC7 unless overridden
+#endif
+#ifndef B2BU_TILE_ASTC
+#define B2BU_TILE_ASTC 3584
+#endif
+#ifndef B2BU_TILE_BC7
+#define B2BU_TILE_BC7 B2BU_TILE16
 #endif
 #ifndef B2BU_TILE_RGBA
 #define B2BU_TILE_RGBA 1536
 #endif
 #ifndef B2BU_TILE_ETC1
-#define B2BU_TILE_ETC1 3584     // 8 B of staged output per block and slot beside the input
+#define B2BU_TILE_ETC1 3072
 #endif
 #ifndef B2BU_SORT_WARPS
 #define B2BU_SORT_WARPS 8
@@ -169,7 +176,8 @@ template <int TARGET> struct PipeCfg {
     static constexpr int NS = 2;                   // data slots: one being worked on, one being stored / loaded
     static constexpr int NO = B2BU_ORDER_SLOTS;    // order slots: how far the sorter may run ahead
     static constexpr bool DYNAMIC = TARGET != TGT_ASTC;
-    static constexpr int TILE = TARGET == TGT_RGBA ? B2BU_TILE_RGBA : TARGET == TGT_ETC1 ? B2BU_TILE_ETC1 : B2BU_TILE16;
+    static constexpr int TILE = TARGET == TGT_RGBA ? B2BU_TILE_RGBA : TARGET == TGT_ETC1 ? B2BU_TILE_ETC1
+                              : TARGET == TGT_ASTC ? B2BU_TILE_ASTC : TARGET == TGT_BC7 ? B2BU_TILE_BC7 : B2BU_TILE16;
     static constexpr int SORT_WARPS = B2BU_SORT_WARPS;
     static constexpr int SORT_THREADS = SORT_WARPS * 32;
     static constexpr int WORK_WARPS = B2BU_WORK_WARPS;

@@ -1,8 +1,13 @@
-python bench.py --gpus 1 --steps 20 --warmup 5 --configs none > gpurun_out/b1.json 2>/dev/null
-python bench.py --gpus 1 --steps 200 --warmup 5 --configs none --all-targets > gpurun_out/b2.json 2>/dev/null
-python - <<'PY'
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python bench.py --all-targets --no-cpu-baseline --steps 200 --e2e-steps 2 --configs none 2>/dev/null | tail -1 > gpurun_out/all_targets.json
+python -c "
 import json
-for f in ("b1","b2"):
-    d=json.loads(open("gpurun_out/%s.json"%f).read().strip().splitlines()[-1])
-    print(f, "ms", round(d["ms_per_step"]*1e3,2), "median(separated)", round(d["ms_per_step_median"]*1e3,2), d["timing"]["per_step_us_min"], d["timing"]["per_step_us_max"], "frac", round(d["roofline"]["frac"],3), round(d["per_path_roofline"]["frac_of_per_path_roofline"],3), {k.split("/")[0]:round(v["us_per_launch"],1) for k,v in d.get("extra",{}).items() if "shuffled" in k})
-PY
+d=json.loads(open('gpurun_out/all_targets.json').read())
+print(round(d['ms_per_step']*1e3,2), round(d['ms_per_step_median']*1e3,2), ' '.join('%s=%.1f'%(k.replace('kat-',''),v['us_per_launch']) for k,v in d['extra'].items()))
+"
+timeout 600 python bench.py 2>/dev/null | tail -1 > gpurun_out/bench_default.json
+python -c "
+import json
+d=json.loads(open('gpurun_out/bench_default.json').read())
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline'])
+"
