@@ -46,9 +46,15 @@ __host__ __device__ inline uint64_t etc1s_row_state_bytes(uint32_t nbx)
 // over the SMs first and packed only when there are more slices than SMs; row_cap: widest slice whose previous-row state
 // fits in shared memory (wider slices keep it in the scratch area); table_set: the host keeps kEtc1sTableSets sets of
 // first-level tables of growing size (see etc1s_host.cu) and the launch takes the largest one that fits beside the pipelines.
+// helpers: with at most two slices per SM every pipeline gets kEtc1sHelpers more warps that decode all bit positions ahead
+// of the tokenizer (the speculation ring, etc1s_kernels.cu); 0 = the two-warp pipeline.
 constexpr int kEtc1sTableSets = 3;
-struct Etc1sDecodePlan { int pipes; uint32_t row_cap; int table_set; };
-Etc1sDecodePlan plan_etc1s_decode(uint32_t num_slices, uint32_t max_nbx, int sm_count, const uint32_t l1_words[kEtc1sTableSets]);
+#ifndef B2BU_K2_HELPERS
+#define B2BU_K2_HELPERS 6
+#endif
+constexpr int kEtc1sHelpers = B2BU_K2_HELPERS;
+struct Etc1sDecodePlan { int pipes; uint32_t row_cap; int table_set; int helpers; };
+Etc1sDecodePlan plan_etc1s_decode(uint32_t num_slices, uint32_t max_nbx, int sm_count, const uint32_t l1_words[kEtc1sTableSets], bool is_video);
 cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, const Etc1sDecodePlan& plan, cudaStream_t stream);
 cudaError_t launch_etc1s_gather_etc1(const uint32_t* idx, uint64_t nblocks, const uint32_t* endpoints, const uint32_t* sel_etc1, void* out,
                                      int sm_count, cudaStream_t stream);

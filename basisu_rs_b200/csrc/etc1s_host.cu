@@ -280,7 +280,7 @@ static int etc1s_run(b2bu_etc1s* h, int target, const std::vector<SliceReq>& sli
     P.scratch = static_cast<uint8_t*>(h->d_scratch);
     uint32_t l1_words[kEtc1sTableSets];
     for (int k = 0; k < kEtc1sTableSets; k++) l1_words[k] = h->l1_ofs[k][4];
-    const Etc1sDecodePlan dplan = plan_etc1s_decode((uint32_t)ns, max_nbx, c->sm_count, l1_words);
+    const Etc1sDecodePlan dplan = plan_etc1s_decode((uint32_t)ns, max_nbx, c->sm_count, l1_words, h->is_video);
     const int set = dplan.table_set;
     h->last_set = set;
     P.l1 = h->d_l1[set];

@@ -53,8 +53,44 @@ struct alignas(16) PipeShared {
     uint32_t ring[kRingWords + kHalfBytes / 4];
     uint2 tok[kTokRounds][kRound];                // tokenizer -> resolver
     uint16_t hist[64];                            // selector history when it fits (it always does for real files)
+    uint2 hdesc[kRound];                          // resolver: shared addresses of the entries of the round's history references
+    uint16_t hres[kRound];                        //           ... and what they read
     uint64_t bar_full[kTokRounds], bar_empty[kTokRounds];
     uint32_t abort, pad;                          // set by the resolver when it has found an error
+};
+
+// ---- speculation ring ("wide" pipelines: at most two slices per SM, so there are warps to spare) ----
+// The only thing the tokenizer's chain really needs from a table read is the CODE LENGTH at the current bit position.
+// Helper warps decode every bit position of the stream against the three hot models ahead of the tokenizer -- one lane per
+// position, no dependence between positions -- and leave (length, symbol) per position and model in shared memory.  The
+// tokenizer's link becomes  LDS.U8 [q + table] -> IADD  (measured: 28-34 cycles against 44-62 for LDS -> SHF -> LOP3 ->
+// IMAD, tools/probe_chase.cu), with the symbol fetched by a second load that nothing waits for.
+constexpr int kSpecPos = 4096;                    // bit positions in the ring
+constexpr int kSpecChunk = 256;                   // positions per helper work item
+constexpr int kSpecChunks = kSpecPos / kSpecChunk;
+constexpr int kSpecMirrorChunks = 5;              // the ring's first chunks are repeated behind it: the reader wraps at sync points only
+constexpr int kSpecMirror = kSpecMirrorChunks * kSpecChunk;
+constexpr int kSpecAhead = 6;                     // chunks that must be complete from the reader's chunk on at a sync point
+// between two sync points (one per round, and after every slow pair) the fast path reads at most 16 pairs = 16 * (16 + 2 * 32)
+// = 1280 bits on from where it is
+static_assert(255 + 1280 < kSpecAhead * kSpecChunk && 1280 <= kSpecMirror && kSpecAhead < kSpecChunks, "speculation ring sync distance");
+// entry: symbol in the low half, flags in byte 2, code size * 4 in byte 3 (0 for anything the fast path does not take)
+constexpr uint32_t kSpecSpecial = 1u << 16;       // no code, run symbol, symbol above 16 bits
+constexpr uint32_t kSpecDelta0 = 1u << 22;        // predictor symbols only: the first / second block of the pair has predictor 3
+constexpr uint32_t kSpecDelta1 = 1u << 23;
+constexpr uint32_t kSpecTableBytes = (kSpecPos + kSpecMirror) * 4u;   // distance between the three tables of a ring
+// The four tables of a ring, per bit position p:
+//   0  endpoint_pred symbol at p            2  selector symbol at p
+//   1  delta_endpoint symbol at p FOLLOWED BY the selector symbol behind it: delta symbol | flags | both code sizes (x 4)
+//   3  that selector symbol | the delta's own code size (x 4) in byte 3 (for blocks inside a selector run)
+// so a block costs the tokenizer ONE link whether it has a delta symbol or not.
+struct alignas(16) SpecShared {
+    uint32_t ent[4][kSpecPos + kSpecMirror];
+    uint32_t stage[kEtc1sHelpers > 0 ? kEtc1sHelpers : 1][kSpecChunk + 32];   // a helper's selector entries of its chunk and the 32 positions behind it
+    uint32_t done[kSpecChunks];                   // chunk c complete: done[c % kSpecChunks] == c + 1
+    uint32_t consumed;                            // the reader is at or beyond this chunk
+    uint32_t raw_loaded;                          // bytes of the slice that have reached the compressed-byte ring
+    uint32_t stop, pad;
 };
 
 // 64 buffered stream bits (hi:lo, `avail` valid, zeros above), the next ring word already loaded, and `pre`: the low
@@ -153,12 +189,12 @@ __device__ __forceinline__ void piece_store(uint32_t* ring, uint32_t piece, int 
 
 #ifdef B2BU_K2_TRACE
 // tuning aid (never in the product build): per-slice cycle / event counters of the two stages
-__device__ unsigned long long g_k2trace[64][8];
+__device__ unsigned long long g_k2trace[64][16];
 #define K2T(slot, v) do { if (lane == 0 && trace_slice < 64u) g_k2trace[trace_slice][(slot)] += (unsigned long long)(v); } while (0)
-#define K2T_DECL(x) x
+#define K2T_DECL(...) __VA_ARGS__
 #else
 #define K2T(slot, v) do { } while (0)
-#define K2T_DECL(x)
+#define K2T_DECL(...)
 #endif
 
 __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
@@ -426,6 +462,358 @@ static __device__ void etc1s_tokenize(const Etc1sDecodeParams& P, const Etc1sSli
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Wide pipelines, stage 0: helper warps fill the speculation ring.  Helper h of H takes chunks h, h + H, ...
+// ---------------------------------------------------------------------------------------------------
+// First-level entry -> speculation entry.  A code longer than the first-level table (size 0, flagged) is looked up in the
+// reference's flat table in global memory HERE, off the tokenizer's chain: the helpers have the time, so in wide pipelines
+// only run symbols and invalid codes are left to the slow path.  v: the 32 stream bits from this position on.
+__device__ __forceinline__ uint32_t spec_entry(uint32_t e, uint32_t v, const uint32_t* __restrict__ flat, uint32_t max_len, uint32_t run_sym, bool is_pred)
+{
+    uint32_t sym = e >> 8, len = e & 31u;
+    if ((e & kL1Special) != 0u) {
+        if (len != 0u) return kSpecSpecial;                                   // a run symbol
+        const uint32_t f = __ldg(flat + (v & ((1u << max_len) - 1u)));      // huffman.rs:186-198
+        sym = f >> 5; len = f & 31u;
+        if (len == 0u || sym == run_sym) return kSpecSpecial;
+    }
+    if (len == 0u || sym > 0xFFFFu) return kSpecSpecial;
+    uint32_t r = (len << 26) | sym;
+    if (is_pred) r |= ((sym & 3u) == 3u ? kSpecDelta0 : 0u) | ((sym & 12u) == 12u ? kSpecDelta1 : 0u);
+    return r;
+}
+
+static __device__ void etc1s_speculate(const Etc1sDecodeParams& P, PipeShared& W, SpecShared& S, const uint32_t* l1s, uint32_t helper, uint32_t helpers, int lane)
+{
+    const uint32_t* t0 = l1s + P.l1_ofs[0];
+    const uint32_t* t1 = l1s + P.l1_ofs[1];
+    const uint32_t* t2 = l1s + P.l1_ofs[2];
+    const uint32_t m0 = (1u << P.l1_bits[0]) - 1u, m1 = (1u << P.l1_bits[1]) - 1u, m2 = (1u << P.l1_bits[2]) - 1u;
+    const uint32_t rle_sym = (P.hist_size + (P.num_selectors & 0xFFFFu)) & 0xFFFFu;       // mod.rs:220-222 (u16 arithmetic)
+    volatile uint32_t* consumed = &S.consumed;
+    volatile uint32_t* raw_loaded = &S.raw_loaded;
+    volatile uint32_t* stop = &S.stop;
+    for (uint32_t c = helper;; c += helpers) {
+        // the ring slot must be free (the reader is past chunk c - kSpecChunks) and the chunk's bytes (and the word after) resident
+        const uint32_t need_bytes = c * (kSpecChunk / 8) + kSpecChunk / 8 + 8u;
+        while (!(c < *consumed + (uint32_t)kSpecChunks && need_bytes <= *raw_loaded)) {
+            if (*stop) return;
+            __nanosleep(64);
+        }
+        asm volatile("" ::: "memory");
+        const uint32_t slot = c % kSpecChunks;
+        uint32_t* stage = S.stage[helper];
+        uint32_t ep[kSpecChunk / 32], ed[kSpecChunk / 32];
+#pragma unroll
+        for (int g = 0; g <= kSpecChunk / 32; g++) {
+            const uint32_t w = (c * (kSpecChunk / 32) + (uint32_t)g) % (uint32_t)kRingWords;     // (the ring's first piece is mirrored behind it)
+            const uint32_t v = __funnelshift_r(W.ring[w], W.ring[w + 1u], (uint32_t)lane);
+            stage[g * 32 + lane] = spec_entry(t2[v & m2], v, P.flat[2], P.max_len[2], rle_sym, false);
+            if (g < kSpecChunk / 32) {
+                ep[g] = spec_entry(t0[v & m0], v, P.flat[0], P.max_len[0], 256u, true);
+                ed[g] = spec_entry(t1[v & m1], v, P.flat[1], P.max_len[1], 0xFFFFFFFFu, false);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < kSpecChunk / 32; g++) {
+            const uint32_t i = slot * kSpecChunk + (uint32_t)g * 32u + (uint32_t)lane;
+            const uint32_t es = stage[g * 32 + lane], d = ed[g];
+            const uint32_t es2 = stage[g * 32 + lane + (d >> 26)];                               // the selector symbol behind this delta symbol
+            const bool bad = ((d | es2) & kSpecSpecial) != 0u;
+            const uint32_t da = bad ? ((d & 0xFFFFu) | kSpecSpecial) : ((d & 0xFFFFu) | ((d & 0xFF000000u) + (es2 & 0xFF000000u)));
+            const uint32_t db = (es2 & 0xFFFFu) | (d & 0xFF000000u);
+            S.ent[0][i] = ep[g]; S.ent[1][i] = da; S.ent[2][i] = es; S.ent[3][i] = db;
+            if (slot < (uint32_t)kSpecMirrorChunks) { S.ent[0][i + kSpecPos] = ep[g]; S.ent[1][i + kSpecPos] = da; S.ent[2][i + kSpecPos] = es; S.ent[3][i + kSpecPos] = db; }
+        }
+        __syncwarp();                                                                            // the stage is reused by the next chunk
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&S.done[slot]) = c + 1u;
+    }
+}
+
+// One predicated read of a speculation entry: the code size (x 4) for the chain and the whole word for the token.
+__device__ __forceinline__ void spec_ld(uint32_t addr, uint32_t on, uint32_t& len4, uint32_t& e)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %3, 0;\nmov.u32 %0, 0;\nmov.u32 %1, 0;\n@p ld.shared.u8 %0, [%2+3];\n@p ld.shared.u32 %1, [%2];\n}\n"
+                 : "=&r"(len4), "=&r"(e) : "r"(addr), "r"(on) : "memory");
+}
+// ... and of a predictor symbol's entry: when it is skipped (inside a repeat run) `e` keeps the previous symbol's word
+__device__ __forceinline__ void spec_ld_keep(uint32_t addr, uint32_t on, uint32_t& len4, uint32_t& e)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %3, 0;\nmov.u32 %0, 0;\n@p ld.shared.u8 %0, [%2+3];\n@p ld.shared.u32 %1, [%2];\n}\n"
+                 : "=&r"(len4), "+r"(e) : "r"(addr), "r"(on) : "memory");
+}
+
+struct WideState { uint32_t q, sel_rle, pred_rep, prev_e; };      // q: 4 * position in the speculation ring; prev_e: entry of the last predictor symbol
+struct WideConsts { uint32_t ent_p, num_selectors; };             // ent_p: shared address of the ring's first table
+
+// The wide form of fast_pairs: same tokens, same "anything unusual -> false, nothing written".
+template <bool EVEN, int NP>
+__device__ __forceinline__ bool fast_pairs_wide(WideState& st, const WideConsts& K, uint2* tk, uint32_t& grp)
+{
+    uint32_t a = st.q + K.ent_p, spec = 0u, sel_rle = st.sel_rle, pred_rep = st.pred_rep, prev_e = st.prev_e, syms = 0u;
+    uint2 t[2 * NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        uint32_t cur, d0, d1;
+        if (EVEN) {
+            const uint32_t rep = pred_rep != 0u ? 1u : 0u;
+            uint32_t l0;
+            spec_ld_keep(a, rep ^ 1u, l0, prev_e);
+            a += l0;
+            spec |= prev_e;
+            cur = prev_e & 0xFFu;
+            d0 = prev_e & kSpecDelta0; d1 = prev_e & kSpecDelta1;
+            pred_rep -= rep;
+            syms |= cur << (8 * p);
+        } else {
+            cur = (grp >> (4 * p)) & 15u;
+            d0 = (cur & 3u) == 3u ? 1u : 0u; d1 = (cur & 12u) == 12u ? 1u : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            uint32_t l1, e1, l2, e2;
+            asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %3, 0;\nmov.u32 %0, 0;\nmov.u32 %1, 0;\n@p ld.shared.u8 %0, [%2+%4];\n@p ld.shared.u32 %1, [%2+%5];\n}\n"
+                         : "=&r"(l1), "=&r"(e1) : "r"(a), "r"(j ? d1 : d0), "n"(3u * kSpecTableBytes + 3u), "n"(kSpecTableBytes) : "memory");
+            a += l1;
+            const uint32_t run = sel_rle != 0u ? 1u : 0u;
+            spec_ld(a + 2u * kSpecTableBytes, run ^ 1u, l2, e2);
+            a += l2;
+            spec |= e1 | e2;
+            sel_rle -= run;
+            t[2 * p + j] = make_uint2((run ? K.num_selectors : (e2 & 0xFFFFu)) | (((cur >> (2 * j)) & 3u) << 16), e1 & 0xFFFFu);
+        }
+    }
+    if (spec & kSpecSpecial) return false;
+#pragma unroll
+    for (int i = 0; i < 2 * NP; i += 2) *reinterpret_cast<uint4*>(tk + i) = make_uint4(t[i].x, t[i].y, t[i + 1].x, t[i + 1].y);
+    st.q = a - K.ent_p; st.sel_rle = sel_rle; st.pred_rep = pred_rep; st.prev_e = prev_e;
+    if (EVEN) grp = syms;
+    return true;
+}
+
+// The same for kLeanPairs pairs while no run is active (runs only start in the slow path): every selector and predictor
+// symbol is read, so only the delta read is conditional -- and that one is predicated together with its add, nothing has
+// to be zeroed.  One running address; the three tables sit at constant distances (immediates of the loads), so a link is
+// LDS.U8 -> IADD -> LDS.U8.  (A lone warp issues slowly: the instruction count matters here as much as the chain.)
+constexpr int kLeanPairs = 4;
+template <bool EVEN>
+__device__ __forceinline__ bool lean_pairs(WideState& st, const WideConsts& K, uint2* tk, uint32_t& grp)
+{
+    uint32_t a = st.q + K.ent_p, spec = 0u, prev_e = st.prev_e, syms = 0u, e1 = 0u;
+    uint2 t[2 * kLeanPairs];
+#pragma unroll
+    for (int p = 0; p < kLeanPairs; p++) {
+        uint32_t cur, d0, d1;
+        if (EVEN) {
+            uint32_t l0;
+            asm volatile("ld.shared.u8 %0, [%2+3];\nld.shared.u32 %1, [%2];\n" : "=&r"(l0), "=&r"(prev_e) : "r"(a) : "memory");
+            a += l0;
+            spec |= prev_e;
+            cur = prev_e & 0xFFu;
+            d0 = prev_e & kSpecDelta0; d1 = prev_e & kSpecDelta1;
+            syms |= cur << (8 * p);
+        } else {
+            cur = (grp >> (4 * p)) & 15u;
+            d0 = (cur & 3u) == 3u ? 1u : 0u; d1 = (cur & 12u) == 12u ? 1u : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            uint32_t l, e2;
+            // with a delta symbol: table 1 (both symbols' sizes, the delta symbol) + table 3 (the selector symbol behind it);
+            // without: table 2.  Exactly one of the two groups runs, so `l` and `e2` are always written.
+            asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %5, 0;\n"
+                         "@p ld.shared.u8 %0, [%4+%6];\n@p ld.shared.u32 %2, [%4+%7];\n@p ld.shared.u16 %1, [%4+%8];\n"
+                         "@!p ld.shared.u8 %0, [%4+%9];\n@!p ld.shared.u32 %1, [%4+%10];\n"
+                         "@p or.b32 %3, %3, %2;\n}\n"
+                         : "=&r"(l), "=&r"(e2), "+r"(e1), "+r"(spec)
+                         : "r"(a), "r"(j ? d1 : d0), "n"(kSpecTableBytes + 3u), "n"(kSpecTableBytes), "n"(3u * kSpecTableBytes),
+                           "n"(2u * kSpecTableBytes + 3u), "n"(2u * kSpecTableBytes) : "memory");
+            a += l;
+            spec |= e2;                                                               // (table 3 entries have no flag bits in the low half... and the u16 load reads only that)
+            t[2 * p + j] = make_uint2((e2 & 0xFFFFu) | (((cur >> (2 * j)) & 3u) << 16), e1 & 0xFFFFu);
+        }
+    }
+    if (spec & kSpecSpecial) return false;
+#pragma unroll
+    for (int i = 0; i < 2 * kLeanPairs; i += 2) *reinterpret_cast<uint4*>(tk + i) = make_uint4(t[i].x, t[i].y, t[i + 1].x, t[i + 1].y);
+    st.q = a - K.ent_p; st.prev_e = prev_e;
+    if (EVEN) grp = syms;
+    return true;
+}
+
+// Wide pipelines, stage 1.  The position is (base_pos + q / 4) in bits; the bit buffer of the narrow tokenizer only exists
+// while pair_slow runs (rebuilt from the compressed-byte ring at the current position, and turned back into a position).
+static __device__ void etc1s_tokenize_wide(const Etc1sDecodeParams& P, const Etc1sSliceJob& job, PipeShared& W, SpecShared& S, const uint32_t* l1s,
+                                           unsigned long long* predrow, int lane, uint32_t trace_slice)
+{
+    const uint8_t* __restrict__ data = P.data + job.data_ofs;
+    const uint32_t nbx = job.nbx, nby = job.nby;
+    auto opaque = [](uint32_t v) -> uint32_t { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; };
+    const uint32_t l1_base = smem_u32(l1s);
+    TokConsts K;
+    K.t0 = opaque(l1_base + 4u * P.l1_ofs[0]); K.t1 = opaque(l1_base + 4u * P.l1_ofs[1]);
+    K.t2 = opaque(l1_base + 4u * P.l1_ofs[2]); K.t3 = opaque(l1_base + 4u * P.l1_ofs[3]);
+    K.m0 = opaque((1u << P.l1_bits[0]) - 1u); K.m1 = opaque((1u << P.l1_bits[1]) - 1u);
+    K.m2 = opaque((1u << P.l1_bits[2]) - 1u); K.m3 = opaque((1u << P.l1_bits[3]) - 1u);
+    K.num_selectors = opaque(P.num_selectors & 0xFFFFu);
+    K.rle_sym = opaque((P.hist_size + K.num_selectors) & 0xFFFFu);
+    K.is_video = opaque(P.is_video);
+    uint32_t* ring = W.ring;
+    K.ring_base = opaque(smem_u32(ring));
+    WideConsts KW;
+    KW.ent_p = opaque(smem_u32(S.ent[0]));
+    KW.num_selectors = K.num_selectors;
+
+    uint32_t loaded = 0;
+    for (; loaded < 3; loaded++) { uint4 r[2]; piece_load(data, job.data_len, loaded, lane, r); piece_store(ring, loaded, lane, r); }
+    __threadfence_block();
+    __syncwarp();
+
+    // single-lane shared-memory stores without a divergent region (a lone warp pays ~50 cycles for every BSSY / BSYNC pair)
+    auto st_lane0 = [&](void* p, uint32_t v) {
+        asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %2, 0;\n@p st.volatile.shared.u32 [%0], %1;\n}\n" ::"r"(smem_u32(p)), "r"(v), "r"(lane) : "memory");
+    };
+    st_lane0(&S.raw_loaded, loaded * (uint32_t)kHalfBytes);
+
+    WideState ws;
+    ws.q = 0u; ws.sel_rle = 0u; ws.pred_rep = 0u; ws.prev_e = 0u;
+    uint32_t base_chunk = 0u;                     // chunk index of q == 0 (the position is base_chunk * kSpecChunk + q / 4 bits)
+    uint32_t done_upto = 0u;                      // chunks [0, done_upto) are known to be complete
+    uint32_t terr = 0u;
+    bool gone = false;                            // the resolver has aborted
+    uint32_t round = 0;
+    K2T_DECL(const long long tt0 = clock64(); uint32_t n_slow = 0; uint32_t n_sym = 0; long long t_wait = 0; long long t_lean = 0; uint32_t n_lean = 0;)
+
+    // wrap, and wait until the fast path's reach from here is covered by complete chunks
+    auto sync_point = [&]() {
+        while (ws.q >= (uint32_t)kSpecPos * 4u) { ws.q -= (uint32_t)kSpecPos * 4u; base_chunk += (uint32_t)kSpecChunks; }
+        const uint32_t here = base_chunk + (ws.q >> 2) / (uint32_t)kSpecChunk;
+        st_lane0(&S.consumed, here);                                                   // nothing before this chunk is looked at again
+        const uint32_t need = here + (uint32_t)kSpecAhead;
+        while (done_upto < need) {
+            K2T_DECL(const long long w0 = clock64();)
+            while (ld_volatile_shared(&S.done[done_upto % kSpecChunks]) != done_upto + 1u)
+                if (ld_volatile_shared(&W.abort)) { gone = true; return; }
+            K2T_DECL(t_wait += clock64() - w0;)
+            done_upto++;
+        }
+        asm volatile("" ::: "memory");
+    };
+    // the reference's control flow for one pair, from and back to the position
+    auto slow_pair = [&](uint2* tk, uint32_t nblk, uint32_t even_row, uint32_t cur) -> uint32_t {
+        const uint32_t pos = (base_chunk % (uint32_t)(kRingWords * 32 / kSpecChunk)) * (uint32_t)kSpecChunk + (ws.q >> 2);     // modulo the byte ring
+        const uint32_t w = (pos >> 5) % (uint32_t)kRingWords, sh = pos & 31u;
+        TokState st;
+        st.bs.lo = __funnelshift_r(ring[w], ring[w + 1u], sh);
+        st.bs.hi = ring[w + 1u] >> sh;
+        st.bs.pre = st.bs.lo; st.bs.x = 64u - sh; st.bs.nw = ring[w + 2u]; st.bs.raddr = K.ring_base + 4u * (w + 3u);
+        const uint32_t raddr0 = st.bs.raddr, x0 = st.bs.x;
+        st.sel_rle = ws.sel_rle; st.pred_rep = ws.pred_rep; st.prev_sym = ws.prev_e & 0xFFu; st.cur = cur; st.terr = 0u;
+        st = pair_slow(st, K, P, tk, nblk, even_row);
+        const uint32_t used = ((st.bs.raddr - raddr0) << 3) + x0 - (st.bs.x & 0xFFu);
+        ws.q += used << 2;
+        ws.sel_rle = st.sel_rle; ws.pred_rep = st.pred_rep;
+        const uint32_t ps = st.prev_sym & 0xFFu;
+        ws.prev_e = ps | ((ps & 3u) == 3u ? kSpecDelta0 : 0u) | ((ps & 12u) == 12u ? kSpecDelta1 : 0u);
+        terr = st.terr;
+        return st.cur;
+    };
+    // the general form of a lean step: two fast steps of two pairs, each falling back to the slow path pair by pair
+    auto general_step = [&](uint2* tk4, bool even, uint32_t& grp4) {
+        constexpr int NP = 2;
+        const uint32_t g4 = grp4;
+        if (even) grp4 = 0u;
+        for (uint32_t h = 0; h < (uint32_t)kLeanPairs && !terr && !gone; h += NP) {
+            uint32_t grp = even ? 0u : (g4 >> (4u * h)) & ((1u << (4 * NP)) - 1u);
+            const uint32_t g0 = grp;
+            if (!(even ? fast_pairs_wide<true, NP>(ws, KW, tk4 + 2u * h, grp) : fast_pairs_wide<false, NP>(ws, KW, tk4 + 2u * h, grp))) {
+                K2T_DECL(n_slow++;)
+                if (even) grp = 0u;
+                for (int i = 0; i < NP && !terr && !gone; i++) {
+                    const uint32_t c = slow_pair(tk4 + 2u * (h + i), 2u, even ? 1u : 0u, even ? 0u : (g0 >> (4 * i)) & 15u);
+                    if (even) grp |= c << (8 * i);
+                    sync_point();                                                     // a slow pair may have read run lengths: re-establish the reach
+                }
+            }
+            if (even) grp4 |= grp << (8u * h);
+        }
+    };
+
+    for (uint32_t y = 0; y < nby; y++) {
+        const bool even = (y & 1u) == 0u;
+        for (uint32_t x0 = 0; x0 < nbx; x0 += kRound, round++) {
+            const uint32_t nb = nbx - x0 < (uint32_t)kRound ? nbx - x0 : (uint32_t)kRound;
+            const uint32_t slot = round % kTokRounds, use = round / kTokRounds;
+            if (round >= (uint32_t)kTokRounds) {
+                K2T_DECL(const long long w0 = clock64();)
+                while (!mbar_try_wait_once(&W.bar_empty[slot], (use - 1u) & 1u))
+                    if (ld_volatile_shared(&W.abort)) return;
+                K2T_DECL(t_wait += clock64() - w0;)
+            }
+            sync_point();
+            if (gone) return;
+            const uint32_t piece = (base_chunk + (ws.q >> 2) / (uint32_t)kSpecChunk) / (uint32_t)(8 * kHalfBytes / kSpecChunk);
+            const bool fetch = loaded < piece + 3u;                                 // warp-uniform
+            uint4 pre[2];
+            if (fetch) piece_load(data, job.data_len, loaded, lane, pre);
+
+            uint2* tk = W.tok[slot];
+            const uint32_t npairs = (nb + 1u) >> 1;
+            if (nb == (uint32_t)kRound) {
+                uint32_t nlo = 0u, nhi = 0u;                                          // next row's predictor bits: pair i at bits 4 i .. 4 i + 3
+                const unsigned long long curp = even ? 0ull : predrow[x0 >> 5];
+                const uint32_t clo = (uint32_t)curp, chi = (uint32_t)(curp >> 32);
+#pragma unroll 1
+                for (int q = 0; q < kRound / 2; q += kLeanPairs) {
+                    uint32_t grp4 = ((q < 8 ? clo : chi) >> (4 * (q & 7))) & ((1u << (4 * kLeanPairs)) - 1u);
+                    bool ok = (ws.sel_rle | ws.pred_rep) == 0u;
+                    K2T_DECL(const long long l0 = clock64();)
+                    if (ok) ok = even ? lean_pairs<true>(ws, KW, tk + 2 * q, grp4) : lean_pairs<false>(ws, KW, tk + 2 * q, grp4);
+                    K2T_DECL(t_lean += clock64() - l0; n_lean++;)
+                    if (!ok) {                                                        // a run is active or something unusual is ahead
+                        general_step(tk + 2 * q, even, grp4);
+                        if (gone) return;
+                        if (terr) break;
+                    }
+                    if (even) {                                                       // the high nibble of each pair's symbol belongs to the row below
+                        uint32_t n = (grp4 >> 4) & 0x0F0F0F0Fu;
+                        n = (n | (n >> 4)) & 0x00FF00FFu;
+                        n = (n | (n >> 8)) & 0xFFFFu;
+                        if (q < 8) nlo |= n << (4 * (q & 7)); else nhi |= n << (4 * (q & 7));
+                    }
+                }
+                if (even) asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %3, 0;\n@p st.v2.u32 [%0], {%1, %2};\n}\n" ::"l"(predrow + (x0 >> 5)), "r"(nlo), "r"(nhi), "r"(lane) : "memory");
+            } else if (even) {
+                unsigned long long nextp = 0ull;
+                for (uint32_t q = 0; q < npairs; q++) {
+                    const uint32_t c = slow_pair(tk + 2u * q, 2u * q + 1u < nb ? 2u : 1u, 1u, 0u);
+                    if (terr) break;
+                    nextp = (nextp >> 4) | ((unsigned long long)(c >> 4) << 60);    // pair q ends up at bits 4q .. 4q+3
+                }
+                if (lane == 0) predrow[x0 >> 5] = nextp >> (4u * (16u - npairs));
+            } else {
+                unsigned long long curp = predrow[x0 >> 5];
+                for (uint32_t q = 0; q < npairs; q++) {
+                    slow_pair(tk + 2u * q, 2u * q + 1u < nb ? 2u : 1u, 0u, (uint32_t)curp & 15u);
+                    curp >>= 4;
+                    if (terr) break;
+                }
+            }
+            K2T_DECL(n_sym += nb;)
+            if (fetch) { piece_store(ring, loaded, lane, pre); loaded++; __threadfence_block(); }
+            __syncwarp();
+            if (fetch) st_lane0(&S.raw_loaded, loaded * (uint32_t)kHalfBytes);
+            asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %1, 0;\n@p mbarrier.arrive.shared::cta.b64 _, [%0];\n}\n" ::"r"(smem_u32(&W.bar_full[slot])), "r"(lane) : "memory");
+            if (terr) return;
+        }
+    }
+    K2T(14, t_lean); K2T(15, n_lean);
+    K2T(0, clock64() - tt0); K2T(1, t_wait); K2T(2, n_sym); K2T(3, n_slow);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Stage 2: resolver warp.  rowep: endpoint index of every block of the previous row.
 // ---------------------------------------------------------------------------------------------------
 static __device__ void etc1s_resolve(const Etc1sDecodeParams& P, const Etc1sSliceJob& job, PipeShared& W, uint16_t* rowep, uint16_t* hist,
@@ -439,7 +827,7 @@ static __device__ void etc1s_resolve(const Etc1sDecodeParams& P, const Etc1sSlic
     for (uint32_t i = lane; i < hist_size; i += 32) hist[i] = 0;                   // mod.rs:616-621
     __syncwarp();
     uint32_t rover = hist_size / 2, prev_ep = 0, carry_up = 0, round = 0;
-    K2T_DECL(const long long tt0 = clock64(); long long t_wait = 0; uint32_t n_hit = 0; uint32_t n_serial = 0;)
+    K2T_DECL(const long long tt0 = clock64(); long long t_wait = 0; uint32_t n_hit = 0; uint32_t n_serial = 0; long long t_seg[4] = {0, 0, 0, 0};)
 
     for (uint32_t y = 0; y < nby; y++) {
         for (uint32_t x0 = 0; x0 < nbx; x0 += kRound, round++) {
@@ -456,7 +844,7 @@ static __device__ void etc1s_resolve(const Etc1sDecodeParams& P, const Etc1sSlic
             carry_up = up_last;
             K2T_DECL(const long long w0 = clock64();)
             mbar_wait(&W.bar_full[slot], use & 1u);
-            K2T_DECL(t_wait += clock64() - w0;)
+            K2T_DECL(t_wait += clock64() - w0; const long long s0 = clock64();)
             uint2 tok = make_uint2(0u, 0u);
             if ((uint32_t)lane < nb) tok = W.tok[slot][lane];
             __syncwarp();
@@ -474,6 +862,7 @@ static __device__ void etc1s_resolve(const Etc1sDecodeParams& P, const Etc1sSlic
             }
 
             // ---- endpoints: f_b(prev) = const c (up / up-left / video 0), prev (left) or (prev + d) mod n ----
+            K2T_DECL(const long long s1 = clock64(); t_seg[0] += s1 - s0;)
             uint32_t ep;
             const bool live = (uint32_t)lane < nv;
             const bool scan_ok = scan_ok_n && !__any_sync(0xFFFFFFFFu, live && pred == 3u && d >= num_endpoints);
@@ -510,30 +899,55 @@ static __device__ void etc1s_resolve(const Etc1sDecodeParams& P, const Etc1sSlic
             if (nv > 0u) prev_ep = __shfl_sync(0xFFFFFFFFu, ep, nv - 1u);
 
             // ---- selectors: the history buffer is the serial part (mod.rs:399-426, :610-640) ----
+            K2T_DECL(const long long s2 = clock64(); t_seg[1] += s2 - s1;)
             uint32_t sel = 0u;
-            if (!is_video && hist_size > 0u && hist_size <= 64u && nv == (uint32_t)kRound) {
-                uint16_t* hs = W.hist;                                               // (named so that the accesses compile to LDS / STS)
-                // straight-line form for full rounds: a codebook index is "store sym at the rover", a history reference is
-                // "swap entries k and k/2" (k = 0 swaps with itself); both are two loads and two stores at selected addresses
-                uint32_t herr = 32u;
-#pragma unroll 8
-                for (uint32_t b = 0; b < (uint32_t)kRound; b++) {
-                    const uint32_t sym = __shfl_sync(0xFFFFFFFFu, tok.x, b) & 0xFFFFu;
-                    const bool hit = sym >= num_selectors;
-                    uint32_t k = sym - num_selectors;
-                    const bool bad = hit && k >= hist_size;                          // assert mod.rs:409
-                    herr = bad && b < herr ? b : herr;
-                    k = hit && !bad ? k : rover;
-                    const uint32_t kh = hit ? k >> 1 : rover;
-                    const uint32_t v = hs[k], t = hs[kh];
-                    hs[k] = (uint16_t)(hit ? t : sym);                               // every lane stores the same values
-                    hs[kh] = (uint16_t)(hit ? v : sym);
-                    const uint32_t s = hit ? v : sym;
-                    const uint32_t r1 = rover + 1u == hist_size ? hist_size / 2 : rover + 1u;
-                    rover = hit ? rover : r1;
-                    if ((uint32_t)lane == b) sel = s;
+            const uint32_t sym_l = tok.x & 0xFFFFu;
+            const bool hit_l = sym_l >= num_selectors;
+            // a round without real history references (index 0 -- the run repeat -- swaps with itself and entry 0 is outside the
+            // rover's range [size / 2, size) when size >= 2): the inserts are a scatter, everything else reads entry 0
+            if (!is_video && hist_size >= 2u && hist_size <= 64u && nv == (uint32_t)kRound &&
+                __ballot_sync(0xFFFFFFFFu, hit_l && sym_l != num_selectors) == 0u) {
+                uint16_t* hs = W.hist;
+                const uint32_t ins = __ballot_sync(0xFFFFFFFFu, !hit_l);
+                const uint32_t n_ins = (uint32_t)__popc(ins), r = (uint32_t)__popc(ins & ((1u << lane) - 1u));
+                const uint32_t half = hist_size / 2u, period = hist_size - half;
+                const uint32_t first = hs[0];
+                __syncwarp();
+                if (!hit_l && r + period >= n_ins) hs[half + (rover - half + r) % period] = (uint16_t)sym_l;    // the last store to a slot wins
+                rover = half + (rover - half + n_ins) % period;
+                sel = hit_l ? first : sym_l;
+            } else if (!is_video && hist_size == 64u && nv == (uint32_t)kRound &&
+                       __ballot_sync(0xFFFFFFFFu, hit_l && sym_l - num_selectors >= hist_size) == 0u) {
+                // Full round with history references (none out of range, mod.rs:409), the usual 64-entry buffer.  Only the
+                // references are serial: an insert's slot follows from the number of inserts before it, 32 inserts never meet in
+                // the rover's 32 slots, and no reference reads a slot before the inserts ahead of it have landed if the inserts
+                // are stored segment by segment -- the segment in front of reference j just before its loads.  A lone warp pays
+                // 5-6 cycles per instruction whatever it is, so the loop runs over the references only (compacted through
+                // shared memory) and holds nine instructions: a reference is "swap entries k and k / 2".
+                uint16_t* hs = W.hist;
+                const uint32_t k_l = sym_l - num_selectors;
+                const uint32_t any_k1 = __ballot_sync(0xFFFFFFFFu, hit_l && k_l == 1u);          // only index 1 changes entry 0
+                const bool ser_l = hit_l && (k_l != 0u || any_k1 != 0u);
+                const uint32_t ser = __ballot_sync(0xFFFFFFFFu, ser_l), ins = __ballot_sync(0xFFFFFFFFu, !hit_l);
+                const uint32_t lt = (1u << lane) - 1u;
+                const uint32_t n_ser = (uint32_t)__popc(ser), seg_l = (uint32_t)__popc(ser & lt);
+                const uint32_t n_ins = (uint32_t)__popc(ins), slot_l = 32u + ((rover - 32u + (uint32_t)__popc(ins & lt)) & 31u);
+                const uint32_t hs_base = smem_u32(hs);
+                const uint32_t first = hs[0];
+                if (ser_l) W.hdesc[seg_l] = make_uint2(hs_base + 2u * k_l, hs_base + 2u * (k_l >> 1));
+                __syncwarp();
+                const uint32_t my_slot = hs_base + 2u * slot_l, hres = smem_u32(W.hres);
+#pragma unroll 4
+                for (uint32_t j = 0; j < n_ser; j++) {
+                    const uint2 dsc = W.hdesc[j];
+                    asm volatile("{\n.reg .pred p;\n.reg .u32 v, t;\nsetp.eq.u32 p, %3, %4;\n@p st.shared.u16 [%5], %6;\n"
+                                 "ld.shared.u16 v, [%0];\nld.shared.u16 t, [%1];\nst.shared.u16 [%0], t;\nst.shared.u16 [%1], v;\nst.shared.u16 [%2], v;\n}\n"
+                                 ::"r"(dsc.x), "r"(dsc.y), "r"(hres + 2u * j), "r"(hit_l ? 0xFFFFFFFFu : seg_l), "r"(j), "r"(my_slot), "r"(sym_l) : "memory");
                 }
-                if (herr < 32u && (uint32_t)lane == herr) { const uint32_t k5 = ((herr << 3 | PH_HISTORY) << 8) | ETC1S_ERR_PREDICTION; key = k5 < key ? k5 : key; }
+                if (!hit_l && seg_l == n_ser) hs[slot_l] = (uint16_t)sym_l;
+                __syncwarp();
+                rover = 32u + ((rover - 32u + n_ins) & 31u);
+                sel = ser_l ? W.hres[seg_l] : hit_l ? first : sym_l;
             } else
             for (uint32_t b = 0; b < nv; b++) {
                 const uint32_t a = __shfl_sync(0xFFFFFFFFu, tok.x, b);
@@ -555,6 +969,7 @@ static __device__ void etc1s_resolve(const Etc1sDecodeParams& P, const Etc1sSlic
                 }
                 if ((uint32_t)lane == b) sel = s;
             }
+            K2T_DECL(const long long s3 = clock64(); t_seg[2] += s3 - s2;)
             if (live && (ep >= num_endpoints || sel >= num_selectors)) {             // asserts mod.rs:443-444
                 const uint32_t k6 = (((uint32_t)lane << 3 | PH_RANGE) << 8) | ETC1S_ERR_RANGE;
                 key = k6 < key ? k6 : key;
@@ -570,26 +985,35 @@ static __device__ void etc1s_resolve(const Etc1sDecodeParams& P, const Etc1sSlic
                 rowep[x] = (uint16_t)ep;
             }
             __syncwarp();
+            K2T_DECL(t_seg[3] += clock64() - s3;)
         }
     }
     if (lane == 0) *status = 0u;
+    K2T(8, t_seg[0]); K2T(9, t_seg[1]); K2T(10, t_seg[2]); K2T(11, t_seg[3]);
     K2T(4, clock64() - tt0); K2T(5, t_wait); K2T(6, n_hit); K2T(7, n_serial);
 }
 
-// `pipes` slice pipelines per CTA: warps [0, pipes) tokenize, warps [pipes, 2 pipes) resolve.  The per-slice row state
-// lives in shared memory when the slice is at most `row_cap` blocks wide, else in the global scratch area.
-__global__ void __launch_bounds__(512) etc1s_entropy_decode_kernel(const __grid_constant__ Etc1sDecodeParams P, uint32_t pipes, uint32_t row_cap)
+// `pipes` slice pipelines per CTA: warps [0, pipes) tokenize, warps [pipes, 2 pipes) resolve, and with `helpers` > 0 (wide
+// pipelines) warps [2 pipes, (2 + helpers) pipes) fill the speculation rings.  The per-slice row state lives in shared memory
+// when the slice is at most `row_cap` blocks wide, else in the global scratch area.
+__global__ void __launch_bounds__(512) etc1s_entropy_decode_kernel(const __grid_constant__ Etc1sDecodeParams P, uint32_t pipes, uint32_t row_cap, uint32_t helpers)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* l1s = reinterpret_cast<uint32_t*>(smem_raw);
     const uint32_t l1_words = P.l1_ofs[4];
     PipeShared* pipe_all = reinterpret_cast<PipeShared*>(smem_raw + (((size_t)l1_words * 4 + 15) & ~(size_t)15));
-    unsigned char* rows_all = reinterpret_cast<unsigned char*>(pipe_all + pipes);
+    SpecShared* spec_all = reinterpret_cast<SpecShared*>(pipe_all + pipes);
+    unsigned char* rows_all = helpers ? reinterpret_cast<unsigned char*>(spec_all + pipes) : reinterpret_cast<unsigned char*>(pipe_all + pipes);
     for (uint32_t i = threadIdx.x; i < l1_words; i += blockDim.x) l1s[i] = P.l1[i];
     if (threadIdx.x < pipes) {
         PipeShared& W = pipe_all[threadIdx.x];
         for (int r = 0; r < kTokRounds; r++) { mbar_init(&W.bar_full[r], 1); mbar_init(&W.bar_empty[r], 1); }
         W.abort = 0u;
+        if (helpers) {
+            SpecShared& S = spec_all[threadIdx.x];
+            for (int i = 0; i < kSpecChunks; i++) S.done[i] = 0u;
+            S.consumed = 0u; S.raw_loaded = 0u; S.stop = 0u;
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -607,8 +1031,15 @@ __global__ void __launch_bounds__(512) etc1s_entropy_decode_kernel(const __grid_
     unsigned long long* predrow = reinterpret_cast<unsigned long long*>(rows + ((((size_t)job.nbx + 7u) & ~(size_t)7u) * 2u));
     if (job.nbx <= row_cap) predrow = reinterpret_cast<unsigned long long*>(rows + ((((size_t)row_cap + 7u) & ~(size_t)7u) * 2u));
     uint16_t* hist = P.hist_size <= 64u ? W.hist : reinterpret_cast<uint16_t*>(P.scratch + job.scratch_ofs + etc1s_row_state_bytes(job.nbx));
-    if (role == 0u) etc1s_tokenize(P, job, W, l1s, predrow, lane, slice);
-    else etc1s_resolve(P, job, W, rowep, hist, P.out_idx + job.out_ofs, P.status + slice, lane, slice);
+    if (role == 0u) {
+        if (helpers) {
+            SpecShared& S = spec_all[pipe];
+            etc1s_tokenize_wide(P, job, W, S, l1s, predrow, lane, slice);
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&S.stop) = 1u;     // on every way out: the helpers poll it
+        } else etc1s_tokenize(P, job, W, l1s, predrow, lane, slice);
+    } else if (role == 1u) etc1s_resolve(P, job, W, rowep, hist, P.out_idx + job.out_ofs, P.status + slice, lane, slice);
+    else etc1s_speculate(P, W, spec_all[pipe], l1s, role - 2u, helpers, lane);
 }
 
 // K3a: mod.rs:163-181 -- ETC1S block = [R5<<3, G5<<3, B5<<3, inten<<5 | inten<<2 | 3, selector etc1 bytes]
@@ -745,36 +1176,40 @@ __global__ void __launch_bounds__(256) etc1s_gather_rgba_kernel(const uint32_t* 
 }
 
 // shared memory of K2: first-level tables + per pipeline {PipeShared, previous-row state for row_cap blocks}
-static size_t etc1s_decode_smem_bytes(uint32_t l1_words, int pipes, uint32_t row_cap)
+static size_t etc1s_decode_smem_bytes(uint32_t l1_words, int pipes, uint32_t row_cap, int helpers)
 {
-    return (((size_t)l1_words * 4 + 15) & ~(size_t)15) + (size_t)pipes * (sizeof(PipeShared) + etc1s_row_state_bytes(row_cap));
+    return (((size_t)l1_words * 4 + 15) & ~(size_t)15) + (size_t)pipes * (sizeof(PipeShared) + (helpers ? sizeof(SpecShared) : 0) + etc1s_row_state_bytes(row_cap));
 }
 
 constexpr size_t kK2SmemLimit = 224 * 1024;
 
-Etc1sDecodePlan plan_etc1s_decode(uint32_t num_slices, uint32_t max_nbx, int sm_count, const uint32_t l1_words[kEtc1sTableSets])
+Etc1sDecodePlan plan_etc1s_decode(uint32_t num_slices, uint32_t max_nbx, int sm_count, const uint32_t l1_words[kEtc1sTableSets], bool is_video)
 {
     Etc1sDecodePlan plan;
     int pipes = (int)((num_slices + (uint32_t)sm_count - 1u) / (uint32_t)(sm_count > 0 ? sm_count : 1));
     if (pipes < 1) pipes = 1;
     if (pipes > 8) pipes = 8;                                 // 512 threads: the tokenizer wants more than 64 registers
     uint32_t row_cap = (max_nbx + 31u) & ~31u;
+    // wide pipelines (helper warps + speculation ring) when there are at most two slices per SM; texture video has no fast path
+    int helpers = (pipes <= 2 && !is_video) ? kEtc1sHelpers : 0;
+    if (helpers && etc1s_decode_smem_bytes(l1_words[0], pipes, row_cap, helpers) > kK2SmemLimit) helpers = 0;
     // the largest table set that fits beside `pipes` pipelines with their row state in shared memory; failing that, the
     // smallest set with the row state in global scratch and as many pipelines as fit
     int set = kEtc1sTableSets - 1;
-    while (set > 0 && etc1s_decode_smem_bytes(l1_words[set], pipes, row_cap) > kK2SmemLimit) set--;
-    if (etc1s_decode_smem_bytes(l1_words[set], 1, row_cap) > kK2SmemLimit) row_cap = 0;       // very wide slices
-    while (pipes > 1 && etc1s_decode_smem_bytes(l1_words[set], pipes, row_cap) > kK2SmemLimit) pipes--;
+    while (set > 0 && etc1s_decode_smem_bytes(l1_words[set], pipes, row_cap, helpers) > kK2SmemLimit) set--;
+    if (etc1s_decode_smem_bytes(l1_words[set], 1, row_cap, helpers) > kK2SmemLimit) row_cap = 0;       // very wide slices
+    while (pipes > 1 && etc1s_decode_smem_bytes(l1_words[set], pipes, row_cap, helpers) > kK2SmemLimit) pipes--;
     plan.pipes = pipes;
     plan.row_cap = row_cap;
     plan.table_set = set;
+    plan.helpers = helpers;
     return plan;
 }
 
 cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, const Etc1sDecodePlan& plan, cudaStream_t stream)
 {
     if (P.num_slices == 0) return cudaSuccess;
-    const size_t smem = etc1s_decode_smem_bytes(P.l1_ofs[4], plan.pipes, plan.row_cap);
+    const size_t smem = etc1s_decode_smem_bytes(P.l1_ofs[4], plan.pipes, plan.row_cap, plan.helpers);
     if (smem > kK2SmemLimit) return cudaErrorInvalidValue;                                     // the host sizes the tables to fit
     static bool configured[16] = {};
     int dev = 0;
@@ -785,15 +1220,15 @@ cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, const Etc1sDecodePla
         configured[dev] = true;
     }
     const unsigned grid = (P.num_slices + plan.pipes - 1) / plan.pipes;
-    etc1s_entropy_decode_kernel<<<grid, 64 * plan.pipes, smem, stream>>>(P, (uint32_t)plan.pipes, plan.row_cap);
+    etc1s_entropy_decode_kernel<<<grid, 32 * (2 + plan.helpers) * plan.pipes, smem, stream>>>(P, (uint32_t)plan.pipes, plan.row_cap, (uint32_t)plan.helpers);
     return cudaGetLastError();
 }
 
 #ifdef B2BU_K2_TRACE
 extern "C" __attribute__((visibility("default"))) int b2bu_debug_k2_trace(unsigned long long* dst, int reset)
 {
-    if (reset) { static unsigned long long z[64][8]; return (int)cudaMemcpyToSymbol(g_k2trace, z, sizeof z); }
-    return (int)cudaMemcpyFromSymbol(dst, g_k2trace, sizeof(unsigned long long) * 64 * 8);
+    if (reset) { static unsigned long long z[64][16]; return (int)cudaMemcpyToSymbol(g_k2trace, z, sizeof z); }
+    return (int)cudaMemcpyFromSymbol(dst, g_k2trace, sizeof(unsigned long long) * 64 * 16);
 }
 #endif
 

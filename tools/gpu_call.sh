@@ -1,13 +1,7 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 300 python bench.py --all-targets --no-cpu-baseline --steps 200 --e2e-steps 2 --configs none 2>/dev/null | tail -1 > gpurun_out/all_targets.json
-python -c "
-import json
-d=json.loads(open('gpurun_out/all_targets.json').read())
-print(round(d['ms_per_step']*1e3,2), round(d['ms_per_step_median']*1e3,2), ' '.join('%s=%.1f'%(k.replace('kat-',''),v['us_per_launch']) for k,v in d['extra'].items()))
-"
-timeout 600 python bench.py 2>/dev/null | tail -1 > gpurun_out/bench_default.json
-python -c "
-import json
-d=json.loads(open('gpurun_out/bench_default.json').read())
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline'])
+timeout 600 python -m pytest tests/test_gpu_etc1s.py -x -q 2>&1 | tail -3
+timeout 120 python tools/trace_k2.py libb2bu_k2trace.so 1024 256 8 2>&1 | tail -3
+timeout 300 python bench.py --no-cpu-baseline --steps 20 --e2e-steps 2 --configs c4 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print({k:(v['entropy_ms'],v['parity_vs_oracle']) for k,v in d['configs']['c4_etc1s'].items() if isinstance(v,dict)})
 "

@@ -36,7 +36,7 @@ for rep in range(2):
     st = L.b2bu_etc1s_transcode_slices(dec._h, 3, nbx, nby, data, len(data), ofs, lens, slices, out.ctypes.data, out.size)
     assert st == 0, st
 k2 = ctypes.c_float(); L.b2bu_etc1s_last_timing(dec._h, ctypes.byref(k2), None, None, None)
-tr = np.zeros((64, 8), dtype=np.uint64); L.b2bu_debug_k2_trace(tr.ctypes.data, 0)
+tr = np.zeros((64, 16), dtype=np.uint64); L.b2bu_debug_k2_trace(tr.ctypes.data, 0)
 nblk = nbx * nby
 print("K2 %.2f ms for %d slices of %d blocks (%.1f bits/block)" % (k2.value, slices, nblk, 8.0 * len(one) / nblk))
 for s in (0, slices - 1):
@@ -44,3 +44,5 @@ for s in (0, slices - 1):
     print("slice %d: tokenizer %.0f cyc/block (waiting %.0f%%), %.2f symbols/block, slow path %.2f%% of symbols; "
           "resolver %.0f cyc/block (waiting %.0f%%), history hits %.2f/block, serial endpoint rounds %d"
           % (s, r[0] / nblk, 100 * r[1] / max(r[0], 1), r[2] / nblk, 100 * r[3] / max(r[2], 1), r[4] / nblk, 100 * r[5] / max(r[4], 1), r[6] / nblk, int(r[7])))
+    print("   lean steps: %d, %.0f cycles each (8 blocks)" % (int(r[15]), r[14] / max(r[15], 1)))
+    print("   resolver cycles per round: tokens/checks %.0f, endpoint scan %.0f, selectors %.0f, checks/stores %.0f" % tuple(r[8 + k] * 32 / nblk for k in range(4)))
