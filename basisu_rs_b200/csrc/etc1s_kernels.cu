@@ -56,7 +56,8 @@ struct alignas(16) PipeShared {
     uint2 hdesc[kRound];                          // resolver: shared addresses of the entries of the round's history references
     uint16_t hres[kRound];                        //           ... and what they read
     uint64_t bar_full[kTokRounds], bar_empty[kTokRounds];
-    uint32_t abort, pad;                          // set by the resolver when it has found an error
+    uint32_t abort;                               // set by the resolver when it has found an error
+    uint32_t taken;                               // rounds the resolver has taken out of the token ring (wide pipelines read this instead of bar_empty)
 };
 
 // ---- speculation ring ("wide" pipelines: at most two slices per SM, so there are warps to spare) ----
@@ -190,6 +191,7 @@ __device__ __forceinline__ void piece_store(uint32_t* ring, uint32_t piece, int 
 #ifdef B2BU_K2_TRACE
 // tuning aid (never in the product build): per-slice cycle / event counters of the two stages
 __device__ unsigned long long g_k2trace[64][16];
+__device__ unsigned long long g_k2trace2[64][2];
 #define K2T(slot, v) do { if (lane == 0 && trace_slice < 64u) g_k2trace[trace_slice][(slot)] += (unsigned long long)(v); } while (0)
 #define K2T_DECL(...) __VA_ARGS__
 #else
@@ -464,16 +466,21 @@ static __device__ void etc1s_tokenize(const Etc1sDecodeParams& P, const Etc1sSli
 // ---------------------------------------------------------------------------------------------------
 // Wide pipelines, stage 0: helper warps fill the speculation ring.  Helper h of H takes chunks h, h + H, ...
 // ---------------------------------------------------------------------------------------------------
-// First-level entry -> speculation entry.  A code longer than the first-level table (size 0, flagged) is looked up in the
-// reference's flat table in global memory HERE, off the tokenizer's chain: the helpers have the time, so in wide pipelines
-// only run symbols and invalid codes are left to the slow path.  v: the 32 stream bits from this position on.
-__device__ __forceinline__ uint32_t spec_entry(uint32_t e, uint32_t v, const uint32_t* __restrict__ flat, uint32_t max_len, uint32_t run_sym, bool is_pred)
+// First-level entry -> speculation entry, in two halves so that a helper can have all the global lookups of a chunk in flight
+// at once.  A code longer than the first-level table (size 0, flagged) is looked up in the reference's flat table in global
+// memory HERE, off the tokenizer's chain: the helpers have the time, so in wide pipelines only run symbols and invalid codes
+// are left to the slow path.  v: the 32 stream bits from this position on.
+__device__ __forceinline__ uint32_t spec_flat_lookup(uint32_t e, uint32_t v, const uint32_t* __restrict__ flat, uint32_t max_len)
+{
+    const bool need = (e & kL1Special) != 0u && (e & 31u) == 0u;            // huffman.rs:186-198
+    return need ? (__ldg(flat + (v & ((1u << max_len) - 1u))) | 0x80000000u) : 0u;        // (symbols have 16 bits: bit 31 is free)
+}
+__device__ __forceinline__ uint32_t spec_entry(uint32_t e, uint32_t f, uint32_t run_sym, bool is_pred)
 {
     uint32_t sym = e >> 8, len = e & 31u;
     if ((e & kL1Special) != 0u) {
         if (len != 0u) return kSpecSpecial;                                   // a run symbol
-        const uint32_t f = __ldg(flat + (v & ((1u << max_len) - 1u)));      // huffman.rs:186-198
-        sym = f >> 5; len = f & 31u;
+        sym = (f & 0x7FFFFFFFu) >> 5; len = f & 31u;
         if (len == 0u || sym == run_sym) return kSpecSpecial;
     }
     if (len == 0u || sym > 0xFFFFu) return kSpecSpecial;
@@ -502,28 +509,40 @@ static __device__ void etc1s_speculate(const Etc1sDecodeParams& P, PipeShared& W
         asm volatile("" ::: "memory");
         const uint32_t slot = c % kSpecChunks;
         uint32_t* stage = S.stage[helper];
-        uint32_t ep[kSpecChunk / 32], ed[kSpecChunk / 32];
+        constexpr int G = kSpecChunk / 32;
+        uint32_t ep[G], ed[G], es[G + 1], vv[G + 1];
 #pragma unroll
-        for (int g = 0; g <= kSpecChunk / 32; g++) {
-            const uint32_t w = (c * (kSpecChunk / 32) + (uint32_t)g) % (uint32_t)kRingWords;     // (the ring's first piece is mirrored behind it)
+        for (int g = 0; g <= G; g++) {                                                           // first-level entries
+            const uint32_t w = (c * (uint32_t)G + (uint32_t)g) % (uint32_t)kRingWords;           // (the ring's first piece is mirrored behind it)
             const uint32_t v = __funnelshift_r(W.ring[w], W.ring[w + 1u], (uint32_t)lane);
-            stage[g * 32 + lane] = spec_entry(t2[v & m2], v, P.flat[2], P.max_len[2], rle_sym, false);
-            if (g < kSpecChunk / 32) {
-                ep[g] = spec_entry(t0[v & m0], v, P.flat[0], P.max_len[0], 256u, true);
-                ed[g] = spec_entry(t1[v & m1], v, P.flat[1], P.max_len[1], 0xFFFFFFFFu, false);
+            vv[g] = v;
+            es[g] = t2[v & m2];
+            if (g < G) { ep[g] = t0[v & m0]; ed[g] = t1[v & m1]; }
+        }
+        {
+            uint32_t fp[G], fd[G], fs[G + 1];
+#pragma unroll
+            for (int g = 0; g <= G; g++) {                                                       // the long codes' lookups, all in flight together
+                fs[g] = spec_flat_lookup(es[g], vv[g], P.flat[2], P.max_len[2]);
+                if (g < G) { fp[g] = spec_flat_lookup(ep[g], vv[g], P.flat[0], P.max_len[0]); fd[g] = spec_flat_lookup(ed[g], vv[g], P.flat[1], P.max_len[1]); }
+            }
+#pragma unroll
+            for (int g = 0; g <= G; g++) {
+                stage[g * 32 + lane] = es[g] = spec_entry(es[g], fs[g], rle_sym, false);
+                if (g < G) { ep[g] = spec_entry(ep[g], fp[g], 256u, true); ed[g] = spec_entry(ed[g], fd[g], 0xFFFFFFFFu, false); }
             }
         }
         __syncwarp();
 #pragma unroll
         for (int g = 0; g < kSpecChunk / 32; g++) {
             const uint32_t i = slot * kSpecChunk + (uint32_t)g * 32u + (uint32_t)lane;
-            const uint32_t es = stage[g * 32 + lane], d = ed[g];
+            const uint32_t d = ed[g];
             const uint32_t es2 = stage[g * 32 + lane + (d >> 26)];                               // the selector symbol behind this delta symbol
             const bool bad = ((d | es2) & kSpecSpecial) != 0u;
             const uint32_t da = bad ? ((d & 0xFFFFu) | kSpecSpecial) : ((d & 0xFFFFu) | ((d & 0xFF000000u) + (es2 & 0xFF000000u)));
             const uint32_t db = (es2 & 0xFFFFu) | (d & 0xFF000000u);
-            S.ent[0][i] = ep[g]; S.ent[1][i] = da; S.ent[2][i] = es; S.ent[3][i] = db;
-            if (slot < (uint32_t)kSpecMirrorChunks) { S.ent[0][i + kSpecPos] = ep[g]; S.ent[1][i + kSpecPos] = da; S.ent[2][i + kSpecPos] = es; S.ent[3][i + kSpecPos] = db; }
+            S.ent[0][i] = ep[g]; S.ent[1][i] = da; S.ent[2][i] = es[g]; S.ent[3][i] = db;
+            if (slot < (uint32_t)kSpecMirrorChunks) { S.ent[0][i + kSpecPos] = ep[g]; S.ent[1][i + kSpecPos] = da; S.ent[2][i + kSpecPos] = es[g]; S.ent[3][i + kSpecPos] = db; }
         }
         __syncwarp();                                                                            // the stage is reused by the next chunk
         __threadfence_block();
@@ -598,7 +617,9 @@ __device__ __forceinline__ bool fast_pairs_wide(WideState& st, const WideConsts&
 // to be zeroed.  One running address; the three tables sit at constant distances (immediates of the loads), so a link is
 // LDS.U8 -> IADD -> LDS.U8.  (A lone warp issues slowly: the instruction count matters here as much as the chain.)
 constexpr int kLeanPairs = 4;
-template <bool EVEN>
+// SELRUN: a selector run covers all eight blocks (no selector symbols; a delta symbol's own size comes from table 3);
+// PREDREP (even rows): a predictor repeat run covers all four pairs (no predictor symbols).  Flat image regions are made of these.
+template <bool EVEN, bool SELRUN = false, bool PREDREP = false>
 __device__ __forceinline__ bool lean_pairs(WideState& st, const WideConsts& K, uint2* tk, uint32_t& grp)
 {
     uint32_t a = st.q + K.ent_p, spec = 0u, prev_e = st.prev_e, syms = 0u, e1 = 0u;
@@ -607,10 +628,12 @@ __device__ __forceinline__ bool lean_pairs(WideState& st, const WideConsts& K, u
     for (int p = 0; p < kLeanPairs; p++) {
         uint32_t cur, d0, d1;
         if (EVEN) {
-            uint32_t l0;
-            asm volatile("ld.shared.u8 %0, [%2+3];\nld.shared.u32 %1, [%2];\n" : "=&r"(l0), "=&r"(prev_e) : "r"(a) : "memory");
-            a += l0;
-            spec |= prev_e;
+            if (!PREDREP) {
+                uint32_t l0;
+                asm volatile("ld.shared.u8 %0, [%2+3];\nld.shared.u32 %1, [%2];\n" : "=&r"(l0), "=&r"(prev_e) : "r"(a) : "memory");
+                a += l0;
+                spec |= prev_e;
+            }
             cur = prev_e & 0xFFu;
             d0 = prev_e & kSpecDelta0; d1 = prev_e & kSpecDelta1;
             syms |= cur << (8 * p);
@@ -620,31 +643,139 @@ __device__ __forceinline__ bool lean_pairs(WideState& st, const WideConsts& K, u
         }
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-            uint32_t l, e2;
-            // with a delta symbol: table 1 (both symbols' sizes, the delta symbol) + table 3 (the selector symbol behind it);
-            // without: table 2.  Exactly one of the two groups runs, so `l` and `e2` are always written.
-            asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %5, 0;\n"
-                         "@p ld.shared.u8 %0, [%4+%6];\n@p ld.shared.u32 %2, [%4+%7];\n@p ld.shared.u16 %1, [%4+%8];\n"
-                         "@!p ld.shared.u8 %0, [%4+%9];\n@!p ld.shared.u32 %1, [%4+%10];\n"
-                         "@p or.b32 %3, %3, %2;\n}\n"
-                         : "=&r"(l), "=&r"(e2), "+r"(e1), "+r"(spec)
-                         : "r"(a), "r"(j ? d1 : d0), "n"(kSpecTableBytes + 3u), "n"(kSpecTableBytes), "n"(3u * kSpecTableBytes),
-                           "n"(2u * kSpecTableBytes + 3u), "n"(2u * kSpecTableBytes) : "memory");
-            a += l;
-            spec |= e2;                                                               // (table 3 entries have no flag bits in the low half... and the u16 load reads only that)
-            t[2 * p + j] = make_uint2((e2 & 0xFFFFu) | (((cur >> (2 * j)) & 3u) << 16), e1 & 0xFFFFu);
+            if (SELRUN) {
+                asm volatile("{\n.reg .pred p;\n.reg .u32 l;\nsetp.ne.u32 p, %3, 0;\n@p ld.shared.u8 l, [%0+%4];\n@p ld.shared.u32 %1, [%0+%5];\n@p add.u32 %0, %0, l;\n@p or.b32 %2, %2, %1;\n}\n"
+                             : "+r"(a), "+r"(e1), "+r"(spec) : "r"(j ? d1 : d0), "n"(3u * kSpecTableBytes + 3u), "n"(kSpecTableBytes) : "memory");
+                t[2 * p + j] = make_uint2(K.num_selectors | (((cur >> (2 * j)) & 3u) << 16), e1 & 0xFFFFu);
+            } else {
+                uint32_t l, e2;
+                // with a delta symbol: table 1 (both symbols' sizes, the delta symbol) + table 3 (the selector symbol behind it);
+                // without: table 2.  Exactly one of the two groups runs, so `l` and `e2` are always written -- but ptxas takes two
+                // complementary predicated writes for a partial definition and keeps an "old value" alive (spills, in a kernel of
+                // this size), hence the explicit zero in front.
+                asm volatile("{\n.reg .pred p;\n.reg .b64 zz;\nsetp.ne.u32 p, %5, 0;\nmov.b64 zz, 0;\nmov.b64 {%0, %1}, zz;\n"
+                             "@p ld.shared.u8 %0, [%4+%6];\n@p ld.shared.u32 %2, [%4+%7];\n@p ld.shared.u16 %1, [%4+%8];\n"
+                             "@!p ld.shared.u8 %0, [%4+%9];\n@!p ld.shared.u32 %1, [%4+%10];\n"
+                             "@p or.b32 %3, %3, %2;\n}\n"
+                             : "=&r"(l), "=&r"(e2), "+r"(e1), "+r"(spec)
+                             : "r"(a), "r"(j ? d1 : d0), "n"(kSpecTableBytes + 3u), "n"(kSpecTableBytes), "n"(3u * kSpecTableBytes),
+                               "n"(2u * kSpecTableBytes + 3u), "n"(2u * kSpecTableBytes) : "memory");
+                a += l;
+                spec |= e2;                                                           // (the u16 load from table 3 brings no flag bits)
+                t[2 * p + j] = make_uint2((e2 & 0xFFFFu) | (((cur >> (2 * j)) & 3u) << 16), e1 & 0xFFFFu);
+            }
         }
     }
     if (spec & kSpecSpecial) return false;
 #pragma unroll
     for (int i = 0; i < 2 * kLeanPairs; i += 2) *reinterpret_cast<uint4*>(tk + i) = make_uint4(t[i].x, t[i].y, t[i + 1].x, t[i + 1].y);
     st.q = a - K.ent_p; st.prev_e = prev_e;
+    if (SELRUN) st.sel_rle -= 2u * kLeanPairs;
+    if (EVEN && PREDREP) st.pred_rep -= (uint32_t)kLeanPairs;
     if (EVEN) grp = syms;
     return true;
 }
 
-// Wide pipelines, stage 1.  The position is (base_pos + q / 4) in bits; the bit buffer of the narrow tokenizer only exists
-// while pair_slow runs (rebuilt from the compressed-byte ring at the current position, and turned back into a position).
+// A whole round of lean steps with the state in registers throughout.  Returns the number of steps done (kRound / 2 /
+// kLeanPairs = all); the step it stops in front of has left no trace.  clo / chi: this row's predictor bits (odd rows);
+// nlo / nhi: the bits for the row below (even rows), pair i at bits 4 i .. 4 i + 3.
+template <bool EVEN>
+__device__ __forceinline__ int lean_round(WideState& st, const WideConsts& K, uint2* tk, uint32_t clo, uint32_t chi, uint32_t& nlo, uint32_t& nhi)
+{
+    constexpr int kSteps = kRound / 2 / kLeanPairs;
+#pragma unroll
+    for (int sidx = 0; sidx < kSteps; sidx++) {
+        uint32_t grp = ((sidx < kSteps / 2 ? clo : chi) >> (16 * (sidx % (kSteps / 2)))) & 0xFFFFu;
+        if (!lean_pairs<EVEN>(st, K, tk + 2 * kLeanPairs * sidx, grp)) return sidx;
+        if (EVEN) {                                                                   // the high nibble of each pair's symbol belongs to the row below
+            uint32_t n = (grp >> 4) & 0x0F0F0F0Fu;
+            n = (n | (n >> 4)) & 0x00FF00FFu;
+            n = (n | (n >> 8)) & 0xFFFFu;
+            if (sidx < kSteps / 2) nlo |= n << (16 * (sidx % (kSteps / 2))); else nhi |= n << (16 * (sidx % (kSteps / 2)));
+        }
+    }
+    return kSteps;
+}
+
+// Wide pipelines, stage 1.  The position is (base_chunk * kSpecChunk + q / 4) in bits; the bit buffer of the narrow tokenizer
+// only exists while pair_slow runs (rebuilt from the compressed-byte ring at the current position, and turned back into a
+// position).  Everything off the fast path is out of line and gets / returns the state BY VALUE, so that the fast path's
+// state never has an address (a lone warp cannot hide a single local-memory access).
+#ifdef B2BU_K2_TRACE
+struct WideCtx { WideState ws; uint32_t base_chunk, done_upto, terr, gone, aux, aux2; };
+#else
+struct WideCtx { WideState ws; uint32_t base_chunk, done_upto, terr, gone, aux; };
+#endif   // done_upto: chunks [0, done_upto) are known complete
+
+__device__ __forceinline__ void st_shared_lane0(void* p, uint32_t v, int lane)    // no divergent region: a lone warp pays ~50 cycles for BSSY / BSYNC
+{
+    asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %2, 0;\n@p st.volatile.shared.u32 [%0], %1;\n}\n" ::"r"(smem_u32(p)), "r"(v), "r"(lane) : "memory");
+}
+
+// wrap, tell the helpers where the reader is, and wait until the fast path's reach from here is covered by complete chunks
+__device__ __forceinline__ void wide_sync(WideCtx& c, SpecShared& S, PipeShared& W, int lane)
+{
+    while (c.ws.q >= (uint32_t)kSpecPos * 4u) { c.ws.q -= (uint32_t)kSpecPos * 4u; c.base_chunk += (uint32_t)kSpecChunks; }
+    const uint32_t here = c.base_chunk + (c.ws.q >> 2) / (uint32_t)kSpecChunk;
+    st_shared_lane0(&S.consumed, here, lane);                                          // nothing before this chunk is looked at again
+    const uint32_t need = here + (uint32_t)kSpecAhead;
+    while (c.done_upto < need) {
+        K2T_DECL(const long long w0 = clock64();)
+        while (ld_volatile_shared(&S.done[c.done_upto % kSpecChunks]) != c.done_upto + 1u)
+            if (ld_volatile_shared(&W.abort)) { c.gone = 1u; return; }
+        K2T_DECL(c.aux2 += (uint32_t)(clock64() - w0);)
+        c.done_upto++;
+    }
+    asm volatile("" ::: "memory");
+}
+
+// the reference's control flow for one pair, from and back to the position; aux returns the pair's predictor bits
+__device__ __noinline__ WideCtx wide_slow_pair(WideCtx c, const TokConsts K, const Etc1sDecodeParams& P, const uint32_t* ring, uint2* tk, uint32_t nblk,
+                                               uint32_t even_row, uint32_t cur)
+{
+    const uint32_t pos = (c.base_chunk % (uint32_t)(kRingWords * 32 / kSpecChunk)) * (uint32_t)kSpecChunk + (c.ws.q >> 2);     // modulo the byte ring
+    const uint32_t w = (pos >> 5) % (uint32_t)kRingWords, sh = pos & 31u;
+    TokState st;
+    st.bs.lo = __funnelshift_r(ring[w], ring[w + 1u], sh);
+    st.bs.hi = ring[w + 1u] >> sh;
+    st.bs.pre = st.bs.lo; st.bs.x = 64u - sh; st.bs.nw = ring[w + 2u]; st.bs.raddr = K.ring_base + 4u * (w + 3u);
+    const uint32_t raddr0 = st.bs.raddr, x0 = st.bs.x;
+    st.sel_rle = c.ws.sel_rle; st.pred_rep = c.ws.pred_rep; st.prev_sym = c.ws.prev_e & 0xFFu; st.cur = cur; st.terr = 0u;
+    st = pair_slow(st, K, P, tk, nblk, even_row);
+    const uint32_t used = ((st.bs.raddr - raddr0) << 3) + x0 - (st.bs.x & 0xFFu);
+    c.ws.q += used << 2;
+    c.ws.sel_rle = st.sel_rle; c.ws.pred_rep = st.pred_rep;
+    const uint32_t ps = st.prev_sym & 0xFFu;
+    c.ws.prev_e = ps | ((ps & 3u) == 3u ? kSpecDelta0 : 0u) | ((ps & 12u) == 12u ? kSpecDelta1 : 0u);
+    c.terr = st.terr;
+    c.aux = st.cur;
+    return c;
+}
+
+// the general form of a lean step: two fast steps of two pairs, each falling back to the slow path pair by pair.
+// grp4 in: the step's predictor bits (odd rows); aux out: the four predictor symbols (even rows)
+__device__ __noinline__ WideCtx wide_general_step(WideCtx c, const TokConsts K, const WideConsts KW, const Etc1sDecodeParams& P, SpecShared& S, PipeShared& W,
+                                                  uint2* tk4, uint32_t even, uint32_t grp4, int lane)
+{
+    constexpr int NP = 2;
+    uint32_t out = 0u;
+    for (uint32_t h = 0; h < (uint32_t)kLeanPairs && !c.terr && !c.gone; h += NP) {
+        uint32_t grp = even ? 0u : (grp4 >> (4u * h)) & ((1u << (4 * NP)) - 1u);
+        const uint32_t g0 = grp;
+        if (!(even ? fast_pairs_wide<true, NP>(c.ws, KW, tk4 + 2u * h, grp) : fast_pairs_wide<false, NP>(c.ws, KW, tk4 + 2u * h, grp))) {
+            grp = 0u;
+            for (int i = 0; i < NP && !c.terr && !c.gone; i++) {
+                c = wide_slow_pair(c, K, P, W.ring, tk4 + 2u * (h + i), 2u, even, even ? 0u : (g0 >> (4 * i)) & 15u);
+                grp |= c.aux << (8 * i);
+                wide_sync(c, S, W, lane);                                             // a slow pair may have read run lengths: re-establish the reach
+            }
+        }
+        out |= grp << (8u * h);
+    }
+    c.aux = out;
+    return c;
+}
+
 static __device__ void etc1s_tokenize_wide(const Etc1sDecodeParams& P, const Etc1sSliceJob& job, PipeShared& W, SpecShared& S, const uint32_t* l1s,
                                            unsigned long long* predrow, int lane, uint32_t trace_slice)
 {
@@ -670,91 +801,33 @@ static __device__ void etc1s_tokenize_wide(const Etc1sDecodeParams& P, const Etc
     for (; loaded < 3; loaded++) { uint4 r[2]; piece_load(data, job.data_len, loaded, lane, r); piece_store(ring, loaded, lane, r); }
     __threadfence_block();
     __syncwarp();
+    st_shared_lane0(&S.raw_loaded, loaded * (uint32_t)kHalfBytes, lane);
 
-    // single-lane shared-memory stores without a divergent region (a lone warp pays ~50 cycles for every BSSY / BSYNC pair)
-    auto st_lane0 = [&](void* p, uint32_t v) {
-        asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %2, 0;\n@p st.volatile.shared.u32 [%0], %1;\n}\n" ::"r"(smem_u32(p)), "r"(v), "r"(lane) : "memory");
-    };
-    st_lane0(&S.raw_loaded, loaded * (uint32_t)kHalfBytes);
-
-    WideState ws;
-    ws.q = 0u; ws.sel_rle = 0u; ws.pred_rep = 0u; ws.prev_e = 0u;
-    uint32_t base_chunk = 0u;                     // chunk index of q == 0 (the position is base_chunk * kSpecChunk + q / 4 bits)
-    uint32_t done_upto = 0u;                      // chunks [0, done_upto) are known to be complete
-    uint32_t terr = 0u;
-    bool gone = false;                            // the resolver has aborted
+    WideCtx c;
+    c.ws.q = 0u; c.ws.sel_rle = 0u; c.ws.pred_rep = 0u; c.ws.prev_e = 0u;
+    c.base_chunk = 0u; c.done_upto = 0u; c.terr = 0u; c.gone = 0u; c.aux = 0u;
+    K2T_DECL(c.aux2 = 0u;)
     uint32_t round = 0;
-    K2T_DECL(const long long tt0 = clock64(); uint32_t n_slow = 0; uint32_t n_sym = 0; long long t_wait = 0; long long t_lean = 0; uint32_t n_lean = 0;)
-
-    // wrap, and wait until the fast path's reach from here is covered by complete chunks
-    auto sync_point = [&]() {
-        while (ws.q >= (uint32_t)kSpecPos * 4u) { ws.q -= (uint32_t)kSpecPos * 4u; base_chunk += (uint32_t)kSpecChunks; }
-        const uint32_t here = base_chunk + (ws.q >> 2) / (uint32_t)kSpecChunk;
-        st_lane0(&S.consumed, here);                                                   // nothing before this chunk is looked at again
-        const uint32_t need = here + (uint32_t)kSpecAhead;
-        while (done_upto < need) {
-            K2T_DECL(const long long w0 = clock64();)
-            while (ld_volatile_shared(&S.done[done_upto % kSpecChunks]) != done_upto + 1u)
-                if (ld_volatile_shared(&W.abort)) { gone = true; return; }
-            K2T_DECL(t_wait += clock64() - w0;)
-            done_upto++;
-        }
-        asm volatile("" ::: "memory");
-    };
-    // the reference's control flow for one pair, from and back to the position
-    auto slow_pair = [&](uint2* tk, uint32_t nblk, uint32_t even_row, uint32_t cur) -> uint32_t {
-        const uint32_t pos = (base_chunk % (uint32_t)(kRingWords * 32 / kSpecChunk)) * (uint32_t)kSpecChunk + (ws.q >> 2);     // modulo the byte ring
-        const uint32_t w = (pos >> 5) % (uint32_t)kRingWords, sh = pos & 31u;
-        TokState st;
-        st.bs.lo = __funnelshift_r(ring[w], ring[w + 1u], sh);
-        st.bs.hi = ring[w + 1u] >> sh;
-        st.bs.pre = st.bs.lo; st.bs.x = 64u - sh; st.bs.nw = ring[w + 2u]; st.bs.raddr = K.ring_base + 4u * (w + 3u);
-        const uint32_t raddr0 = st.bs.raddr, x0 = st.bs.x;
-        st.sel_rle = ws.sel_rle; st.pred_rep = ws.pred_rep; st.prev_sym = ws.prev_e & 0xFFu; st.cur = cur; st.terr = 0u;
-        st = pair_slow(st, K, P, tk, nblk, even_row);
-        const uint32_t used = ((st.bs.raddr - raddr0) << 3) + x0 - (st.bs.x & 0xFFu);
-        ws.q += used << 2;
-        ws.sel_rle = st.sel_rle; ws.pred_rep = st.pred_rep;
-        const uint32_t ps = st.prev_sym & 0xFFu;
-        ws.prev_e = ps | ((ps & 3u) == 3u ? kSpecDelta0 : 0u) | ((ps & 12u) == 12u ? kSpecDelta1 : 0u);
-        terr = st.terr;
-        return st.cur;
-    };
-    // the general form of a lean step: two fast steps of two pairs, each falling back to the slow path pair by pair
-    auto general_step = [&](uint2* tk4, bool even, uint32_t& grp4) {
-        constexpr int NP = 2;
-        const uint32_t g4 = grp4;
-        if (even) grp4 = 0u;
-        for (uint32_t h = 0; h < (uint32_t)kLeanPairs && !terr && !gone; h += NP) {
-            uint32_t grp = even ? 0u : (g4 >> (4u * h)) & ((1u << (4 * NP)) - 1u);
-            const uint32_t g0 = grp;
-            if (!(even ? fast_pairs_wide<true, NP>(ws, KW, tk4 + 2u * h, grp) : fast_pairs_wide<false, NP>(ws, KW, tk4 + 2u * h, grp))) {
-                K2T_DECL(n_slow++;)
-                if (even) grp = 0u;
-                for (int i = 0; i < NP && !terr && !gone; i++) {
-                    const uint32_t c = slow_pair(tk4 + 2u * (h + i), 2u, even ? 1u : 0u, even ? 0u : (g0 >> (4 * i)) & 15u);
-                    if (even) grp |= c << (8 * i);
-                    sync_point();                                                     // a slow pair may have read run lengths: re-establish the reach
-                }
-            }
-            if (even) grp4 |= grp << (8u * h);
-        }
-    };
+    uint32_t free_upto = (uint32_t)kTokRounds;    // token slots of rounds [0, free_upto) are known to be free
+    K2T_DECL(const long long tt0 = clock64(); uint32_t n_slow = 0; uint32_t n_sym = 0; long long t_wait = 0; uint32_t n_lean = 0;)
 
     for (uint32_t y = 0; y < nby; y++) {
         const bool even = (y & 1u) == 0u;
         for (uint32_t x0 = 0; x0 < nbx; x0 += kRound, round++) {
             const uint32_t nb = nbx - x0 < (uint32_t)kRound ? nbx - x0 : (uint32_t)kRound;
-            const uint32_t slot = round % kTokRounds, use = round / kTokRounds;
-            if (round >= (uint32_t)kTokRounds) {
+            const uint32_t slot = round % kTokRounds;
+            if (round >= free_upto) {                                               // the resolver counts the rounds it has taken out of the ring
                 K2T_DECL(const long long w0 = clock64();)
-                while (!mbar_try_wait_once(&W.bar_empty[slot], (use - 1u) & 1u))
+                uint32_t taken;
+                while ((taken = ld_volatile_shared(&W.taken)) + (uint32_t)kTokRounds <= round)
                     if (ld_volatile_shared(&W.abort)) return;
+                free_upto = taken + (uint32_t)kTokRounds;
                 K2T_DECL(t_wait += clock64() - w0;)
             }
-            sync_point();
-            if (gone) return;
-            const uint32_t piece = (base_chunk + (ws.q >> 2) / (uint32_t)kSpecChunk) / (uint32_t)(8 * kHalfBytes / kSpecChunk);
+            wide_sync(c, S, W, lane);
+            if (c.gone) return;
+            K2T_DECL(t_wait += c.aux2; c.aux2 = 0u;)
+            const uint32_t piece = (c.base_chunk + (c.ws.q >> 2) / (uint32_t)kSpecChunk) / (uint32_t)(8 * kHalfBytes / kSpecChunk);
             const bool fetch = loaded < piece + 3u;                                 // warp-uniform
             uint4 pre[2];
             if (fetch) piece_load(data, job.data_len, loaded, lane, pre);
@@ -762,55 +835,67 @@ static __device__ void etc1s_tokenize_wide(const Etc1sDecodeParams& P, const Etc
             uint2* tk = W.tok[slot];
             const uint32_t npairs = (nb + 1u) >> 1;
             if (nb == (uint32_t)kRound) {
+                static_assert(kLeanPairs == 4 && kRound == 32, "lean_round's packing of the predictor bits");
+                constexpr int kSteps = kRound / 2 / kLeanPairs;
                 uint32_t nlo = 0u, nhi = 0u;                                          // next row's predictor bits: pair i at bits 4 i .. 4 i + 3
-                const unsigned long long curp = even ? 0ull : predrow[x0 >> 5];
-                const uint32_t clo = (uint32_t)curp, chi = (uint32_t)(curp >> 32);
+                uint32_t clo = 0u, chi = 0u;
+                if (!even) { const uint2 c2 = *reinterpret_cast<const uint2*>(predrow + (x0 >> 5)); clo = c2.x; chi = c2.y; }
+                int sidx = 0;
+                if ((c.ws.sel_rle | c.ws.pred_rep) == 0u) sidx = even ? lean_round<true>(c.ws, KW, tk, clo, chi, nlo, nhi) : lean_round<false>(c.ws, KW, tk, clo, chi, nlo, nhi);
+                K2T_DECL(n_lean += (uint32_t)sidx;)
 #pragma unroll 1
-                for (int q = 0; q < kRound / 2; q += kLeanPairs) {
-                    uint32_t grp4 = ((q < 8 ? clo : chi) >> (4 * (q & 7))) & ((1u << (4 * kLeanPairs)) - 1u);
-                    bool ok = (ws.sel_rle | ws.pred_rep) == 0u;
-                    K2T_DECL(const long long l0 = clock64();)
-                    if (ok) ok = even ? lean_pairs<true>(ws, KW, tk + 2 * q, grp4) : lean_pairs<false>(ws, KW, tk + 2 * q, grp4);
-                    K2T_DECL(t_lean += clock64() - l0; n_lean++;)
-                    if (!ok) {                                                        // a run is active or something unusual is ahead
-                        general_step(tk + 2 * q, even, grp4);
-                        if (gone) return;
-                        if (terr) break;
+                for (; sidx < kSteps; sidx++) {                                       // runs are active, or something unusual is ahead
+                    uint32_t grp4 = ((sidx < kSteps / 2 ? clo : chi) >> (16 * (sidx % (kSteps / 2)))) & 0xFFFFu;
+                    uint2* tk4 = tk + 2 * kLeanPairs * sidx;
+                    const bool sr = c.ws.sel_rle >= 2u * kLeanPairs, s0 = c.ws.sel_rle == 0u;
+                    const bool pr = c.ws.pred_rep >= (uint32_t)kLeanPairs, p0 = c.ws.pred_rep == 0u;
+                    bool ok = false;
+                    if (even) {
+                        if ((sr || s0) && (pr || p0))
+                            ok = sr ? (pr ? lean_pairs<true, true, true>(c.ws, KW, tk4, grp4) : lean_pairs<true, true, false>(c.ws, KW, tk4, grp4))
+                                    : (pr ? lean_pairs<true, false, true>(c.ws, KW, tk4, grp4) : lean_pairs<true, false, false>(c.ws, KW, tk4, grp4));
+                    } else if (sr || s0) ok = sr ? lean_pairs<false, true, false>(c.ws, KW, tk4, grp4) : lean_pairs<false, false, false>(c.ws, KW, tk4, grp4);
+                    if (!ok) {                                                        // the general form
+                        K2T_DECL(n_slow++;)
+                        c = wide_general_step(c, K, KW, P, S, W, tk4, even ? 1u : 0u, grp4, lane);
+                        if (c.gone) return;
+                        if (c.terr) break;
+                        grp4 = c.aux;
                     }
-                    if (even) {                                                       // the high nibble of each pair's symbol belongs to the row below
+                    if (even) {
                         uint32_t n = (grp4 >> 4) & 0x0F0F0F0Fu;
                         n = (n | (n >> 4)) & 0x00FF00FFu;
                         n = (n | (n >> 8)) & 0xFFFFu;
-                        if (q < 8) nlo |= n << (4 * (q & 7)); else nhi |= n << (4 * (q & 7));
+                        if (sidx < kSteps / 2) nlo |= n << (16 * (sidx % (kSteps / 2))); else nhi |= n << (16 * (sidx % (kSteps / 2)));
                     }
                 }
                 if (even) asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %3, 0;\n@p st.v2.u32 [%0], {%1, %2};\n}\n" ::"l"(predrow + (x0 >> 5)), "r"(nlo), "r"(nhi), "r"(lane) : "memory");
             } else if (even) {
                 unsigned long long nextp = 0ull;
                 for (uint32_t q = 0; q < npairs; q++) {
-                    const uint32_t c = slow_pair(tk + 2u * q, 2u * q + 1u < nb ? 2u : 1u, 1u, 0u);
-                    if (terr) break;
-                    nextp = (nextp >> 4) | ((unsigned long long)(c >> 4) << 60);    // pair q ends up at bits 4q .. 4q+3
+                    c = wide_slow_pair(c, K, P, ring, tk + 2u * q, 2u * q + 1u < nb ? 2u : 1u, 1u, 0u);
+                    if (c.terr) break;
+                    nextp = (nextp >> 4) | ((unsigned long long)(c.aux >> 4) << 60);  // pair q ends up at bits 4q .. 4q+3
                 }
                 if (lane == 0) predrow[x0 >> 5] = nextp >> (4u * (16u - npairs));
             } else {
                 unsigned long long curp = predrow[x0 >> 5];
                 for (uint32_t q = 0; q < npairs; q++) {
-                    slow_pair(tk + 2u * q, 2u * q + 1u < nb ? 2u : 1u, 0u, (uint32_t)curp & 15u);
+                    c = wide_slow_pair(c, K, P, ring, tk + 2u * q, 2u * q + 1u < nb ? 2u : 1u, 0u, (uint32_t)curp & 15u);
                     curp >>= 4;
-                    if (terr) break;
+                    if (c.terr) break;
                 }
             }
             K2T_DECL(n_sym += nb;)
             if (fetch) { piece_store(ring, loaded, lane, pre); loaded++; __threadfence_block(); }
             __syncwarp();
-            if (fetch) st_lane0(&S.raw_loaded, loaded * (uint32_t)kHalfBytes);
+            if (fetch) st_shared_lane0(&S.raw_loaded, loaded * (uint32_t)kHalfBytes, lane);
             asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %1, 0;\n@p mbarrier.arrive.shared::cta.b64 _, [%0];\n}\n" ::"r"(smem_u32(&W.bar_full[slot])), "r"(lane) : "memory");
-            if (terr) return;
+            if (c.terr) return;
         }
     }
-    K2T(14, t_lean); K2T(15, n_lean);
-    K2T(0, clock64() - tt0); K2T(1, t_wait); K2T(2, n_sym); K2T(3, n_slow);
+    K2T(0, clock64() - tt0); K2T(1, t_wait); K2T(2, n_sym); K2T(3, n_slow); K2T(15, n_lean);
+    K2T_DECL(if (lane == 0 && trace_slice < 64u) { uint32_t smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); g_k2trace2[trace_slice][0] = smid; g_k2trace2[trace_slice][1] = (unsigned long long)tt0; })
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -848,7 +933,7 @@ static __device__ void etc1s_resolve(const Etc1sDecodeParams& P, const Etc1sSlic
             uint2 tok = make_uint2(0u, 0u);
             if ((uint32_t)lane < nb) tok = W.tok[slot][lane];
             __syncwarp();
-            if (lane == 0) mbar_arrive(&W.bar_empty[slot]);
+            if (lane == 0) { mbar_arrive(&W.bar_empty[slot]); *reinterpret_cast<volatile uint32_t*>(&W.taken) = round + 1u; }
 
             const uint32_t errmask = __ballot_sync(0xFFFFFFFFu, (tok.x & kTokErr) != 0u);
             const uint32_t nv = errmask ? (uint32_t)__ffs((int)errmask) - 1u : nb;  // lanes < nv hold complete tokens
@@ -1008,7 +1093,7 @@ __global__ void __launch_bounds__(512) etc1s_entropy_decode_kernel(const __grid_
     if (threadIdx.x < pipes) {
         PipeShared& W = pipe_all[threadIdx.x];
         for (int r = 0; r < kTokRounds; r++) { mbar_init(&W.bar_full[r], 1); mbar_init(&W.bar_empty[r], 1); }
-        W.abort = 0u;
+        W.abort = 0u; W.taken = 0u;
         if (helpers) {
             SpecShared& S = spec_all[threadIdx.x];
             for (int i = 0; i < kSpecChunks; i++) S.done[i] = 0u;
@@ -1227,7 +1312,8 @@ cudaError_t launch_etc1s_decode(const Etc1sDecodeParams& P, const Etc1sDecodePla
 #ifdef B2BU_K2_TRACE
 extern "C" __attribute__((visibility("default"))) int b2bu_debug_k2_trace(unsigned long long* dst, int reset)
 {
-    if (reset) { static unsigned long long z[64][16]; return (int)cudaMemcpyToSymbol(g_k2trace, z, sizeof z); }
+    if (reset == 1) { static unsigned long long z[64][16]; return (int)cudaMemcpyToSymbol(g_k2trace, z, sizeof z); }
+    if (reset == 2) return (int)cudaMemcpyFromSymbol(dst, g_k2trace2, sizeof(unsigned long long) * 64 * 2);
     return (int)cudaMemcpyFromSymbol(dst, g_k2trace, sizeof(unsigned long long) * 64 * 16);
 }
 #endif
