@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Tuning aid: runs the ETC1S entropy kernel (K2) from a -DB2BU_K2_TRACE build on a config-4 shaped slice and prints
 the per-slice stage counters (cycles per block in each warp, wait shares, slow-path rate).
-usage: trace_k2.py [lib] [blocks_x] [blocks_y] [slices]"""
+usage: trace_k2.py [lib] [blocks_x] [blocks_y] [slices] [flat share | -1 = the benchmark's config-4 set]"""
 import ctypes, os, pathlib, sys
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
@@ -18,15 +18,15 @@ n_cb = 4096
 L = b.lib(); assert L.b2bu_init(0) == 0
 orc = ec.bind(load_oracle())
 ep_cb, sel_cb = make_codebooks(n_cb, n_cb, seed=3)
-flat = float(sys.argv[5]) if len(sys.argv) > 5 else None
-if flat is not None and flat < 0:          # the benchmark's config 4: `slices` different images encoded together
+flat = float(sys.argv[5]) if len(sys.argv) > 5 else None      # none: the synthesiser's default; < 0: the benchmark's config 4
+if flat is not None and flat < 0:          # `slices` different images encoded together, as bench.py does
     eis, sis = [], []
     for k in range(slices):
         e1, s1 = make_indices(nbx, nby, 1, n_cb, n_cb, seed=4 + k, flat=0.15 + 0.45 * ((k * 7) % slices) / max(1, slices - 1))
         eis.append(e1[0]); sis.append(s1[0])
     enc = encode(orc, ep_cb, sel_cb, np.stack(eis), np.stack(sis), nbx, nby, 64, False, False)
     parts, ofs_l, lens_l, pos = [], [], [], 0
-    for k in (range(slices) if flat > -1.5 else range(slices - 1, -1, -1)):      # -2: the same slices in reverse order
+    for k in range(slices):
         one = ec.slice_bytes(enc, k); pad = (-len(one)) % 16
         parts.append(one + b"\0" * pad); ofs_l.append(pos); lens_l.append(len(one)); pos += len(one) + pad
     data = b"".join(parts)
