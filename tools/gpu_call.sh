@@ -1,7 +1,8 @@
-for lib in libb2bu.so libv_prev.so libb2bu.so libv_prev.so; do
-B2BU_LIBRARY=$PWD/basisu_rs_b200/$lib timeout 300 python bench.py --no-cpu-baseline --steps 20 --e2e-steps 2 --configs c4 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('$lib', {k:(round(v['entropy_ms'],2),v['parity_vs_oracle']) for k,v in d['configs']['c4_etc1s'].items() if isinstance(v,dict)})
-"
-done
+set -u
+bash tools/gpu_profile.sh astc > /dev/null 2>&1
+bash tools/gpu_profile_etc1s.sh > /dev/null 2>&1
+timeout 600 python tools/trace_k2.py libb2bu_k2trace.so 1024 1024 64 -1 > gpurun_out/trace_k2_c4.txt 2>&1
+timeout 60 ./tools/bin/probe_chase > gpurun_out/probe_chase.txt 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_default.csv python bench.py --steps 2 --warmup 1 --e2e-steps 1 > gpurun_out/bench_under_ncu.log 2>&1
+ls -la gpurun_out | tail -8
+tail -5 gpurun_out/trace_k2_c4.txt
