@@ -46,7 +46,7 @@ __host__ __device__ inline uint64_t etc1s_row_state_bytes(uint32_t nbx)
 // over the SMs first and packed only when there are more slices than SMs; row_cap: widest slice whose previous-row state
 // fits in shared memory (wider slices keep it in the scratch area); table_set: the host keeps kEtc1sTableSets sets of
 // first-level tables of growing size (see etc1s_host.cu) and the launch takes the largest one that fits beside the pipelines.
-// helpers: with at most two slices per SM every pipeline gets kEtc1sHelpers more warps that decode all bit positions ahead
+// helpers: with at most one slice per SM every pipeline gets kEtc1sHelpers more warps that decode all bit positions ahead
 // of the tokenizer (the speculation ring, etc1s_kernels.cu); 0 = the two-warp pipeline.
 constexpr int kEtc1sTableSets = 3;
 #ifndef B2BU_K2_HELPERS

@@ -4,7 +4,7 @@
 // and selector codebooks and the four slice Huffman models on the host, exactly as the reference
 // does (they are small and serial), then upload them: codebooks as flat u32 arrays, each Huffman
 // model as a 10-bit first-level table for shared memory plus the reference's full flat table.
-// Per call: upload the slice bitstreams, run K2 (one warp per slice) and K3 (gather), copy back.
+// Per call: upload the slice bitstreams, run K2 (one pipeline of warps per slice) and K3 (gather), copy back.
 #include <algorithm>
 #include <cstring>
 #include <memory>

@@ -3,20 +3,22 @@
 // K2  etc1s_entropy_decode: the slice bitstream is one serial chain (reference src/basis_lz/mod.rs:188-458),
 //     but only the BIT POSITION is inherently serial: which table is read next depends on the predictor bits
 //     and the two run counters, never on the endpoint values or on the selector history.  So every slice is
-//     decoded by a two-stage pipeline of two warps connected by a token ring in shared memory:
+//     decoded by a pipeline of warps connected by a token ring in shared memory:
 //
 //       tokenizer warp   walks the bitstream and emits one token per block: predictor (2 bits), the endpoint
 //                        delta symbol, the raw selector symbol (codebook index, history reference or run
-//                        repeat).  Its dependent chain per symbol is  AND -> LDS (first-level table in shared
-//                        memory, up to 15 bits wide) -> funnel shift;  the 32-bit refill, the run counters and
-//                        the token stores are off that chain.  All lanes run the chain redundantly on
-//                        identical state (broadcast shared reads); the lanes are used for the parallel parts:
-//                        staging the compressed bytes into a shared ring with coalesced 16-byte loads.
+//                        repeat).  Two forms.  Narrow (more than one slice per SM, video): the chain per symbol
+//                        is  AND -> LDS (first-level table in shared memory) -> funnel shift, all lanes redundant
+//                        on identical state.  Wide (at most one slice per SM): helper warps decode EVERY bit
+//                        position against the hot models ahead of the tokenizer (one lane per position) and leave
+//                        code size and symbol per position in a shared ring, delta + selector symbol combined,
+//                        so that a block is one  LDS.U8 -> IADD  link of the chain (see the speculation ring below).
 //       resolver warp    turns 32 tokens at a time into (endpoint, selector) pairs: the endpoint predictors
 //                        (left / up / up-left / delta) are a segmented scan over the warp (composition of
-//                        "set to c" and "add d mod n"), the approximate-move-to-front selector history is the
-//                        one remaining serial loop (a shared-memory load and two stores per history hit); then
-//                        one coalesced store of the 32 index words and the row state for the next row.
+//                        "set to c" and "add d mod n"); the approximate-move-to-front selector history is the
+//                        one serial loop and runs over the round's history references only (inserts are a
+//                        scatter whose slots follow from a prefix count); then one coalesced store of the 32
+//                        index words and the row state for the next row.
 //
 //     Errors keep the reference's order: every check has a key (block, phase) and the slice status is the code
 //     of the smallest key over both warps.
@@ -1275,8 +1277,9 @@ Etc1sDecodePlan plan_etc1s_decode(uint32_t num_slices, uint32_t max_nbx, int sm_
     if (pipes < 1) pipes = 1;
     if (pipes > 8) pipes = 8;                                 // 512 threads: the tokenizer wants more than 64 registers
     uint32_t row_cap = (max_nbx + 31u) & ~31u;
-    // wide pipelines (helper warps + speculation ring) when there are at most two slices per SM; texture video has no fast path
-    int helpers = (pipes <= 2 && !is_video) ? kEtc1sHelpers : 0;
+    // wide pipelines (helper warps + speculation ring) when there is at most one slice per SM (two rings do not fit beside
+    // the tables); texture video has no fast path
+    int helpers = (pipes == 1 && !is_video) ? kEtc1sHelpers : 0;
     if (helpers && etc1s_decode_smem_bytes(l1_words[0], pipes, row_cap, helpers) > kK2SmemLimit) helpers = 0;
     // the largest table set that fits beside `pipes` pipelines with their row state in shared memory; failing that, the
     // smallest set with the row state in global scratch and as many pipelines as fit

@@ -1,6 +1,6 @@
-# usage: tools/gpu_call_n.sh N  -- the driver's multi-rank launch of bench.py (both arms)
+# usage: tools/gpu_call_n.sh N  -- the driver's multi-rank launch of bench.py
 N=$1
-timeout 480 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+timeout 560 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
 echo "rc=$?"; tail -3 gpurun_out/bench_n$N.err
 python - <<PY
 import json
