@@ -1,14 +1,7 @@
-timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo rc=$?
-timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo rc=$?
-timeout 600 python bench.py --all-targets --no-cpu-baseline --steps 200 --e2e-steps 20 --configs none > gpurun_out/bench_all_targets.json 2> gpurun_out/bench_all_targets.err; echo rc=$?
-python - <<PY
-import json
-d=json.loads(open("gpurun_out/bench_default.json").read().strip().splitlines()[-1])
-print("default:", d["value"], d["ms_per_step"], d["ms_per_step_median"], "e2e", d["e2e"]["value"], d["e2e"].get("frac_of_pcie_ceiling"), "frac", d["roofline"]["frac"], d["per_path_roofline"]["frac_of_per_path_roofline"], "cpu", d["cpu_baseline"]["value"], "clocks", d["clocks"])
-c=d["configs"]
-print("c3", json.dumps(c.get("c3_bc7_mip_chain"))[:700])
-print("c4", {k:(round(v['entropy_ms'],2), round(v['device_gtexel_s'],2), v['parity_vs_oracle']) for k,v in c['c4_etc1s'].items() if isinstance(v,dict)})
-print("c5", json.dumps(c.get("c5_mixed_batch"))[:1200])
-r=json.loads(open("gpurun_out/bench_ref.json").read().strip().splitlines()[-1]); print("ref:", r["value"], r["ms_per_step"], r["cpu_baseline"])
-a=json.loads(open("gpurun_out/bench_all_targets.json").read().strip().splitlines()[-1]); print("all:", {k:round(v['us_per_launch'],1) for k,v in a['extra'].items()})
-PY
+set -u
+for tool in memcheck initcheck racecheck; do
+  echo "== compute-sanitizer --tool $tool python tools/sanitize_k1_k3.py k2"
+  timeout 600 compute-sanitizer --tool $tool python tools/sanitize_k1_k3.py k2 2>&1 | grep -v "^$" | tail -12
+done > gpurun_out/sanitizer_k2.txt 2>&1
+tail -40 gpurun_out/sanitizer_k2.txt | cut -c1-300
+bash tools/gpu_profile.sh etc1 > /dev/null 2>&1; tail -2 gpurun_out/prof_etc1.log
