@@ -1,7 +1,7 @@
-set -u
-for tool in memcheck initcheck racecheck; do
-  echo "== compute-sanitizer --tool $tool python tools/sanitize_k1_k3.py k2"
-  timeout 600 compute-sanitizer --tool $tool python tools/sanitize_k1_k3.py k2 2>&1 | grep -v "^$" | tail -12
-done > gpurun_out/sanitizer_k2.txt 2>&1
-tail -40 gpurun_out/sanitizer_k2.txt | cut -c1-300
-bash tools/gpu_profile.sh etc1 > /dev/null 2>&1; tail -2 gpurun_out/prof_etc1.log
+for lib in libb2bu.so libv_s6.so libv_s7.so libb2bu.so; do
+B2BU_LIBRARY=$PWD/basisu_rs_b200/$lib timeout 200 python bench.py --all-targets --no-cpu-baseline --steps 200 --e2e-steps 2 --configs none 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('$lib', round(d['ms_per_step']*1e3,2), round(d['ms_per_step_median']*1e3,2), ' '.join('%s=%.1f'%(k.replace('kat-',''),v['us_per_launch']) for k,v in d['extra'].items() if 'shuffled' in k))
+"
+done
