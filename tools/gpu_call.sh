@@ -1,7 +1,7 @@
-for lib in libb2bu.so libv_s6.so libv_s7.so libb2bu.so; do
-B2BU_LIBRARY=$PWD/basisu_rs_b200/$lib timeout 200 python bench.py --all-targets --no-cpu-baseline --steps 200 --e2e-steps 2 --configs none 2>/dev/null | python -c "
+for lib in libb2bu.so libv_tr8.so libb2bu.so libv_tr8.so; do
+B2BU_LIBRARY=$PWD/basisu_rs_b200/$lib timeout 300 python bench.py --no-cpu-baseline --steps 20 --e2e-steps 2 --configs c4 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('$lib', round(d['ms_per_step']*1e3,2), round(d['ms_per_step_median']*1e3,2), ' '.join('%s=%.1f'%(k.replace('kat-',''),v['us_per_launch']) for k,v in d['extra'].items() if 'shuffled' in k))
+print('$lib', {k:(round(v['entropy_ms'],2),v['parity_vs_oracle']) for k,v in d['configs']['c4_etc1s'].items() if isinstance(v,dict)})
 "
 done
