@@ -387,12 +387,15 @@ uastc_sorted_kernel(const uint4* __restrict__ in, void* __restrict__ out, uint32
             // A: classify, rank inside (warp, mode).  Every step is a branch-free pass over all of the thread's blocks (PERS
             // loads / atomics in flight); blocks past the end of a short tile are predicated off.
             const uint32_t myj = blocks_of(nt, bst);            // passes j in which block bst + j * SORT_THREADS is inside the tile
+            // (the twelve unused counters 20..31 all serve as dummy bins, spread over the lanes: in a short tile -- every CTA's
+            // first one -- most of a warp's atomics would otherwise hit ONE address and serialise)
+            const uint32_t dummy = (uint32_t)kBins + (uint32_t)lane % (32u - (uint32_t)kBins);
             const uint32_t* src = stage + (k & 1u) * C::STAGE + bst;
             uint32_t mr[C::PERS];
 #pragma unroll
             for (int j = 0; j < C::PERS; j++) mr[j] = src[j * C::SORT_THREADS] & 127u;      // stale words past the end: discarded below
 #pragma unroll
-            for (int j = 0; j < C::PERS; j++) { const uint32_t lut = T.mode_lut[mr[j]]; mr[j] = (uint32_t)j < myj ? lut : 31u; }   // 31: dummy bin
+            for (int j = 0; j < C::PERS; j++) { const uint32_t lut = T.mode_lut[mr[j]]; mr[j] = (uint32_t)j < myj ? lut : dummy; }  // blocks past the end: a dummy bin
             // the order slot must have been consumed (tile k - NO)
             if (k >= (uint32_t)C::NO) mbar_wait(&bar_ofree[o], (k / C::NO - 1u) & 1u);
             if (st == 0) do { if (k < 6) TRACE(k * 6 + 1); } while (0);

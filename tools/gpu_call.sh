@@ -1,8 +1,8 @@
-for lib in libb2bu.so libv_cl2.so libb2bu.so libv_cl2.so; do
-B2BU_LIBRARY=$PWD/basisu_rs_b200/$lib timeout 200 python bench.py --no-cpu-baseline --steps 20 --e2e-steps 60 --configs none 2>/dev/null | python -c "
+for lib in libb2bu.so libv_dummy.so libb2bu.so libv_dummy.so; do
+B2BU_LIBRARY=$PWD/basisu_rs_b200/$lib timeout 200 python bench.py --all-targets --no-cpu-baseline --steps 200 --e2e-steps 2 --configs none 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('$lib', 'e2e', round(d['e2e']['value'],2), round(d['e2e'].get('frac_of_pcie_ceiling'),3), 'ceiling', round(d['e2e']['pcie_ceiling_gbs'],1), 'parity', d.get('e2e_parity'))
+print('$lib', round(d['ms_per_step']*1e3,2), round(d['ms_per_step_median']*1e3,2), ' '.join('%s=%.1f'%(k.replace('kat-',''),v['us_per_launch']) for k,v in d['extra'].items() if 'shuffled' in k))
 "
 done
-B2BU_LIBRARY=$PWD/basisu_rs_b200/libv_cl2.so timeout 600 python -m pytest tests/test_gpu_uastc.py -x -q 2>&1 | tail -2
+B2BU_LIBRARY=$PWD/basisu_rs_b200/libv_dummy.so timeout 600 python -m pytest tests/test_gpu_uastc.py -x -q 2>&1 | tail -2
