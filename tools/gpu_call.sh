@@ -1,8 +1,7 @@
-for lib in libb2bu.so libv_p0.so libb2bu.so libv_p0.so; do
-B2BU_LIBRARY=$PWD/basisu_rs_b200/$lib timeout 200 python bench.py --all-targets --no-cpu-baseline --steps 200 --e2e-steps 2 --configs none 2>/dev/null | python -c "
+for lib in libb2bu.so libv_pr.so libb2bu.so libv_pr.so; do
+B2BU_LIBRARY=$PWD/basisu_rs_b200/$lib timeout 300 python bench.py --no-cpu-baseline --steps 20 --e2e-steps 2 --configs c4 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('$lib', round(d['ms_per_step']*1e3,2), round(d['ms_per_step_median']*1e3,2), ' '.join('%s=%.1f'%(k.replace('kat-',''),v['us_per_launch']) for k,v in d['extra'].items() if 'shuffled' in k))
+print('$lib', {k:(round(v['entropy_ms'],2),v['parity_vs_oracle']) for k,v in d['configs']['c4_etc1s'].items() if isinstance(v,dict)})
 "
 done
-B2BU_LIBRARY=$PWD/basisu_rs_b200/libv_p0.so timeout 600 python -m pytest tests/test_gpu_uastc.py -x -q 2>&1 | tail -2
