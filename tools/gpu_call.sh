@@ -1,4 +1,4 @@
-for lib in libb2bu.so libv_pr.so libb2bu.so libv_pr.so; do
+for lib in libb2bu.so libv_narrow.so libb2bu.so libv_narrow.so; do
 B2BU_LIBRARY=$PWD/basisu_rs_b200/$lib timeout 300 python bench.py --no-cpu-baseline --steps 20 --e2e-steps 2 --configs c4 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
